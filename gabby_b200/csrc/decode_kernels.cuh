@@ -1,0 +1,447 @@
+// decode_kernels.cuh -- multi-kernel decode path (one CUDA graph per token; any small batch).
+//
+// Every kernel works on R "rows"; a row is one (sequence slot, position) pair: a decode step has
+// one row per sequence, a chunked prefill has several consecutive positions of one sequence.
+// Activations stay fp32 end to end (they are tiny next to the weights); weights and the KV
+// cache are bf16; all dot products accumulate in fp32.
+//
+// No reference counterpart exists (gabby's forward is a stub: /root/reference/src/inference/
+// generator.cc:33-38); the math follows oracle/llama_oracle.cc function by function.
+#pragma once
+#include "common.cuh"
+
+namespace b2l {
+
+// ------------------------------------------------------------------------------------------
+// token embedding gather: h[r][:] = E[token[r]][:]                 (oracle: embedding gather)
+// ------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const uint16_t* __restrict__ E, const int32_t* __restrict__ tokens,
+                             float* __restrict__ h, int H, int V) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.x;
+    int tok = tokens[r];
+    tok = min(max(tok, 0), V - 1);
+    const uint4* src = reinterpret_cast<const uint4*>(E + static_cast<size_t>(tok) * H);
+    float4* dst = reinterpret_cast<float4*>(h + static_cast<size_t>(r) * H);
+    for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+        const uint4 w = __ldg(src + i);
+        dst[2 * i] = make_float4(bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y));
+        dst[2 * i + 1] = make_float4(bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMV: y[b][n] (op)= sum_k W[n][k] * xhat[b][k],  xhat = NORM ? rmsnorm(x) * norm_w : x
+//   MODE 0 store | 1 accumulate into y (residual add) | 2 SwiGLU over (gate,up) row pairs
+// One warp owns two weight rows at a time (the pair, in MODE 2) and streams them with 128-bit
+// L1-bypassing loads; x lives in shared memory as fp32 in K-tiles of `kt` elements.
+// ------------------------------------------------------------------------------------------
+struct GemvArgs {
+    const uint16_t* W;       // [N][K] bf16
+    const float* x;          // [B][ldx]
+    float* y;                // [B][ldy]
+    const uint16_t* norm_w;  // [K] bf16 (NORM only)
+    const float* add;        // optional [B][ldadd]: x <- x + add before use (TP partial-sum fold), may be null
+    float eps;
+    int N, K, ldx, ldy, kt;
+};
+
+constexpr int kGemvThreads = 256;
+constexpr int kGemvWarps = kGemvThreads / 32;
+constexpr int kGemvRowsPerCta = kGemvWarps * 2;
+
+template <int B, int MODE, bool NORM>
+__global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvArgs a) {
+    extern __shared__ __align__(16) float xs[];  // [B][kt]
+    __shared__ float s_red[B][kGemvWarps];
+    __shared__ float s_inv[B];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    pdl_launch_dependents();
+    pdl_wait();
+
+    if (NORM) {
+        // LlamaRMSNorm: inv = rsqrt(mean(x^2) + eps)            (oracle: rmsnorm())
+        float ss[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) ss[b] = 0.f;
+        for (int k = tid * 4; k < a.K; k += kGemvThreads * 4) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const float4 v = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(b) * a.ldx + k);
+                ss[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const float s = warp_sum(ss[b]);
+            if (lane == 0) s_red[b][warp] = s;
+        }
+        __syncthreads();
+        if (tid < B) {
+            float s = 0.f;
+            for (int w = 0; w < kGemvWarps; w++) s += s_red[tid][w];
+            s_inv[tid] = rsqrtf(s / static_cast<float>(a.K) + a.eps);
+        }
+        __syncthreads();
+    }
+
+    const int n_blocks = (a.N + kGemvRowsPerCta - 1) / kGemvRowsPerCta;
+    const int n_tiles = (a.K + a.kt - 1) / a.kt;
+    int loaded_tile = -1;
+
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int row0 = blk * kGemvRowsPerCta + warp * 2;
+        const bool live = row0 < a.N;  // N is even for every Llama shape
+        const uint16_t* w0 = a.W + static_cast<size_t>(live ? row0 : 0) * a.K;
+        const uint16_t* w1 = w0 + a.K;
+        float acc0[B], acc1[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) acc0[b] = acc1[b] = 0.f;
+
+        for (int t = 0; t < n_tiles; t++) {
+            const int k0 = t * a.kt, klen = min(a.kt, a.K - k0);
+            if (loaded_tile != t) {
+                __syncthreads();
+                for (int k = tid * 4; k < klen; k += kGemvThreads * 4) {
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        float4 v = *reinterpret_cast<const float4*>(a.x + static_cast<size_t>(b) * a.ldx + k0 + k);
+                        if (NORM) {
+                            const uint2 nw = *reinterpret_cast<const uint2*>(a.norm_w + k0 + k);
+                            const float inv = s_inv[b];
+                            v.x = bf16lo(nw.x) * (v.x * inv);
+                            v.y = bf16hi(nw.x) * (v.y * inv);
+                            v.z = bf16lo(nw.y) * (v.z * inv);
+                            v.w = bf16hi(nw.y) * (v.w * inv);
+                        }
+                        *reinterpret_cast<float4*>(xs + b * a.kt + k) = v;
+                    }
+                }
+                __syncthreads();
+                loaded_tile = t;
+            }
+            if (live) {
+#pragma unroll 4
+                for (int k = lane * 8; k < klen; k += 256) {
+                    const uint4 wa = ldg_stream(w0 + k0 + k);
+                    const uint4 wb = ldg_stream(w1 + k0 + k);
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        const float4 x0 = *reinterpret_cast<const float4*>(xs + b * a.kt + k);
+                        const float4 x1 = *reinterpret_cast<const float4*>(xs + b * a.kt + k + 4);
+                        acc0[b] = dot8(wa, x0, x1, acc0[b]);
+                        acc1[b] = dot8(wb, x0, x1, acc1[b]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const float s0 = warp_sum(acc0[b]);
+            const float s1 = warp_sum(acc1[b]);
+            if (lane == 0 && live) {
+                if (MODE == 2) {
+                    // silu(gate) * up                               (oracle: MLP block)
+                    a.y[static_cast<size_t>(b) * a.ldy + (row0 >> 1)] = (s0 / (1.0f + __expf(-s0))) * s1;
+                } else if (MODE == 1) {
+                    float* y = a.y + static_cast<size_t>(b) * a.ldy + row0;
+                    y[0] += s0;
+                    y[1] += s1;
+                } else {
+                    float* y = a.y + static_cast<size_t>(b) * a.ldy + row0;
+                    y[0] = s0;
+                    y[1] = s1;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// RoPE (rotate-half, table-driven) on q in place + K/V append into the paged bf16 cache
+//                                                   (oracle: rope_inplace(), KV store with ORC_KV_BF16)
+// ------------------------------------------------------------------------------------------
+struct KvLayout {
+    uint16_t* pool;       // this layer's pool: [num_pages][2][page_size][kvd]
+    int page_size, kvd;   // kvd = local kv heads * head_dim
+    __device__ __forceinline__ uint16_t* at(int page, int which, int off) const {
+        return pool + ((static_cast<size_t>(page) * 2 + which) * page_size + off) * kvd;
+    }
+};
+
+struct RowMeta {
+    const int32_t* positions;     // [R]
+    const int32_t* slots;         // [R] row -> block table row
+    const int32_t* block_tables;  // [n_slots][max_blocks]
+    int max_blocks;
+};
+
+__global__ void rope_kv_kernel(float* __restrict__ qkv, int ld, const float* __restrict__ rope, KvLayout kv,
+                               RowMeta rm, int nh, int nkv, int hd) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.x;
+    const int pos = rm.positions[r];
+    const int half = hd >> 1;
+    const float* cs = rope + static_cast<size_t>(pos) * hd;  // [half][2]
+    const int page = rm.block_tables[static_cast<size_t>(rm.slots[r]) * rm.max_blocks + pos / kv.page_size];
+    const int off = pos % kv.page_size;
+    float* row = qkv + static_cast<size_t>(r) * ld;
+    uint16_t* kdst = kv.at(page, 0, off);
+    uint16_t* vdst = kv.at(page, 1, off);
+    const int qd = nh * hd, kvd = nkv * hd;
+    for (int i = threadIdx.x; i < (nh + nkv) * half; i += blockDim.x) {
+        const int head = i / half, j = i % half;
+        const float c = cs[2 * j], s = cs[2 * j + 1];
+        float* v = row + head * hd;  // q heads then k heads are contiguous in the fused row
+        const float x0 = v[j], x1 = v[j + half];
+        const float y0 = x0 * c - x1 * s, y1 = x1 * c + x0 * s;
+        if (head < nh) {
+            v[j] = y0;
+            v[j + half] = y1;
+        } else {
+            const int kh = head - nh;
+            kdst[kh * hd + j] = f32_to_bf16_bits(y0);
+            kdst[kh * hd + j + half] = f32_to_bf16_bits(y1);
+        }
+    }
+    const float* vsrc = row + qd + kvd;
+    for (int i = threadIdx.x; i < kvd; i += blockDim.x) vdst[i] = f32_to_bf16_bits(vsrc[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// GQA decode attention over the paged cache, split along the context ("split-K"), with the
+// last-arriving CTA of each (row, kv head) merging the splits.
+//                                                   (oracle: causal softmax(q k^T / sqrt(d)) v)
+// grid (nsplit, nkv, R); 128 threads. LPT lanes share one token (8 dims each).
+// ------------------------------------------------------------------------------------------
+struct AttnArgs {
+    const float* qkv;  // [R][ld], q already rotated
+    int ld;
+    KvLayout kv;
+    RowMeta rm;
+    float* part_acc;   // [R][nkv][nsplit][GROUP][HD]
+    float* part_ml;    // [R][nkv][nsplit][GROUP][2]
+    int* counters;     // [R][nkv], zero between launches
+    float* out;        // [R][ldo]  (heads concatenated)
+    int ldo;
+    float scale;
+};
+
+constexpr int kAttnThreads = 128;
+constexpr int kAttnWarps = kAttnThreads / 32;
+
+template <int HD, int GROUP>
+__global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArgs a) {
+    constexpr int LPT = HD / 8;        // lanes per token
+    constexpr int TPW = 32 / LPT;      // tokens per warp step
+    constexpr int NG = kAttnWarps * TPW;  // token groups in the CTA
+    __shared__ float s_m[NG][GROUP], s_l[NG][GROUP];
+    __shared__ float s_acc[NG][GROUP][HD];
+    __shared__ int s_last;
+
+    pdl_launch_dependents();
+    pdl_wait();
+
+    const int split = blockIdx.x, nsplit = gridDim.x, kvh = blockIdx.y, nkv = gridDim.y, r = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sub = lane / LPT, sl = lane % LPT;  // token sub-slot, 8-dim slice
+    const int grp = warp * TPW + sub;
+
+    const int ctx = a.rm.positions[r] + 1;
+    const int chunk = (ctx + nsplit - 1) / nsplit;
+    const int j0 = split * chunk, j1 = min(ctx, j0 + chunk);
+    const int32_t* bt = a.rm.block_tables + static_cast<size_t>(a.rm.slots[r]) * a.rm.max_blocks;
+
+    float q[GROUP][8];
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+        const float* qp = a.qkv + static_cast<size_t>(r) * a.ld + (kvh * GROUP + g) * HD + sl * 8;
+        const float4 q0 = *reinterpret_cast<const float4*>(qp), q1 = *reinterpret_cast<const float4*>(qp + 4);
+        q[g][0] = q0.x * a.scale; q[g][1] = q0.y * a.scale; q[g][2] = q0.z * a.scale; q[g][3] = q0.w * a.scale;
+        q[g][4] = q1.x * a.scale; q[g][5] = q1.y * a.scale; q[g][6] = q1.z * a.scale; q[g][7] = q1.w * a.scale;
+    }
+    float m[GROUP], l[GROUP], acc[GROUP][8];
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+        m[g] = -INFINITY;
+        l[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
+    }
+
+    for (int jb = j0; jb < j1; jb += NG) {
+        const int j = jb + grp;
+        const bool valid = j < j1;
+        uint4 kw = make_uint4(0, 0, 0, 0), vw = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            const int page = bt[j / a.kv.page_size], off = j % a.kv.page_size;
+            kw = *reinterpret_cast<const uint4*>(a.kv.at(page, 0, off) + kvh * HD + sl * 8);
+            vw = *reinterpret_cast<const uint4*>(a.kv.at(page, 1, off) + kvh * HD + sl * 8);
+        }
+        const float kf[8] = {bf16lo(kw.x), bf16hi(kw.x), bf16lo(kw.y), bf16hi(kw.y),
+                             bf16lo(kw.z), bf16hi(kw.z), bf16lo(kw.w), bf16hi(kw.w)};
+        const float vf[8] = {bf16lo(vw.x), bf16hi(vw.x), bf16lo(vw.y), bf16hi(vw.y),
+                             bf16lo(vw.z), bf16hi(vw.z), bf16lo(vw.w), bf16hi(vw.w)};
+#pragma unroll
+        for (int g = 0; g < GROUP; g++) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) s = fmaf(q[g][i], kf[i], s);
+#pragma unroll
+            for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (valid) {
+                const float mn = fmaxf(m[g], s);
+                const float corr = __expf(m[g] - mn), p = __expf(s - mn);
+                l[g] = l[g] * corr + p;
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[g][i] = fmaf(acc[g][i], corr, p * vf[i]);
+                m[g] = mn;
+            }
+        }
+    }
+
+    // merge the NG token groups of this CTA
+#pragma unroll
+    for (int g = 0; g < GROUP; g++) {
+        if (sl == 0) {
+            s_m[grp][g] = m[g];
+            s_l[grp][g] = l[g];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) s_acc[grp][g][sl * 8 + i] = acc[g][i];
+    }
+    __syncthreads();
+    const size_t pbase = (static_cast<size_t>(r) * nkv + kvh) * nsplit + split;
+    for (int e = tid; e < GROUP * HD; e += kAttnThreads) {
+        const int g = e / HD, d = e % HD;
+        float M = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < NG; t++) M = fmaxf(M, s_m[t][g]);
+        float L = 0.f, A = 0.f;
+        if (M > -INFINITY) {
+#pragma unroll
+            for (int t = 0; t < NG; t++) {
+                const float w = __expf(s_m[t][g] - M);  // exp(-inf) = 0 for empty groups
+                L = fmaf(s_l[t][g], w, L);
+                A = fmaf(s_acc[t][g][d], w, A);
+            }
+        }
+        a.part_acc[(pbase * GROUP + g) * HD + d] = A;
+        if (d == 0) {
+            a.part_ml[(pbase * GROUP + g) * 2 + 0] = M;
+            a.part_ml[(pbase * GROUP + g) * 2 + 1] = L;
+        }
+    }
+    // last CTA of this (row, kv head) merges the splits
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int done = atomicAdd(a.counters + r * nkv + kvh, 1);
+        s_last = (done == nsplit - 1);
+        if (s_last) a.counters[r * nkv + kvh] = 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const size_t rbase = (static_cast<size_t>(r) * nkv + kvh) * nsplit;
+    for (int e = tid; e < GROUP * HD; e += kAttnThreads) {
+        const int g = e / HD, d = e % HD;
+        float M = -INFINITY;
+        for (int s = 0; s < nsplit; s++) M = fmaxf(M, __ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2));
+        float L = 0.f, A = 0.f;
+        for (int s = 0; s < nsplit; s++) {
+            const float ms = __ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2);
+            if (ms == -INFINITY) continue;
+            const float w = __expf(ms - M);
+            L = fmaf(__ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2 + 1), w, L);
+            A = fmaf(__ldcg(a.part_acc + ((rbase + s) * GROUP + g) * HD + d), w, A);
+        }
+        a.out[static_cast<size_t>(r) * a.ldo + (kvh * GROUP + g) * HD + d] = A / L;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// greedy argmax (first max) over logits [R][ld]; one CTA per row.       (oracle: orc_argmax)
+// Writes ids[r] = offset + argmax and, when vals != null, the max value (TP shard merge).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int ld, int n, int offset,
+                                                      int32_t* __restrict__ ids, float* __restrict__ vals) {
+    __shared__ unsigned long long s_key[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const float* x = logits + static_cast<size_t>(r) * ld;
+    unsigned long long best = 0ull;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned long long k = argmax_key(x[i], i);
+        best = k > best ? k : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    if ((tid & 31) == 0) s_key[tid >> 5] = best;
+    __syncthreads();
+    if (tid < 32) {
+        best = tid < (blockDim.x >> 5) ? s_key[tid] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (tid == 0) {
+            const int idx = argmax_key_index(best);
+            ids[r] = offset + idx;
+            if (vals) vals[r] = x[idx];
+        }
+    }
+}
+
+// device-resident greedy loop bookkeeping: feed the argmax back, advance positions, log the id
+__global__ void advance_kernel(const int32_t* __restrict__ next_ids, int32_t* __restrict__ tokens,
+                               int32_t* __restrict__ positions, int32_t* __restrict__ out_ids,
+                               int32_t* __restrict__ step_counter, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = threadIdx.x;
+    const int step = *step_counter;
+    if (i < n) {
+        const int32_t id = next_ids[i];
+        tokens[i] = id;
+        positions[i] += 1;
+        out_ids[static_cast<size_t>(step) * n + i] = id;
+    }
+    __syncthreads();
+    if (i == 0) *step_counter = step + 1;
+}
+
+// y[i] += x[i]  (TP: add the all-reduced projection into the residual stream)
+__global__ void add_kernel(float* __restrict__ y, const float* __restrict__ x, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
+// standalone RMSNorm (parity tap of the final norm only; the hot path fuses it into the GEMV)
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const uint16_t* __restrict__ w, float* __restrict__ y,
+                               int H, float eps) {
+    __shared__ float s_red[32];
+    const int r = blockIdx.x;
+    const float* xr = x + static_cast<size_t>(r) * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) ss += xr[i] * xr[i];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); i++) tot += s_red[i];
+    const float inv = rsqrtf(tot / static_cast<float>(H) + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) y[static_cast<size_t>(r) * H + i] = bf16_bits_to_f32(w[i]) * (xr[i] * inv);
+}
+
+}  // namespace b2l

@@ -1,0 +1,766 @@
+// engine.cu -- the b2l C-ABI (include/b2l.h): device context, weight residency, paged KV pool,
+// and the forward pass enqueued as hand-written sm_100a kernels. No CPU fallback anywhere:
+// without a CUDA device b2l_create fails.
+//
+// Reference boundary: this is the missing body of gabby::inference::Llama3Generator::{Load,
+// Generate} (/root/reference/src/inference/generator.cc:33-44); the host C++ layer
+// (gabby_b200/host/) adapts it to the Generator interface.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+
+#include "decode_kernels.cuh"
+#include "synth.cuh"
+
+using namespace b2l;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- tensor naming (HF names as they appear in the safetensors header) --------------------
+enum Kind { K_EMBED, K_FINAL_NORM, K_LM_HEAD, K_IN_NORM, K_Q, K_K, K_V, K_O, K_POST_NORM, K_GATE, K_UP, K_DOWN, K_BAD };
+
+Kind parse_name(const std::string& n, int* layer) {
+    *layer = -1;
+    if (n == "model.embed_tokens.weight") return K_EMBED;
+    if (n == "model.norm.weight") return K_FINAL_NORM;
+    if (n == "lm_head.weight") return K_LM_HEAD;
+    const std::string pre = "model.layers.";
+    if (n.compare(0, pre.size(), pre) != 0) return K_BAD;
+    const size_t dot = n.find('.', pre.size());
+    if (dot == std::string::npos) return K_BAD;
+    *layer = std::atoi(n.substr(pre.size(), dot - pre.size()).c_str());
+    const std::string rest = n.substr(dot + 1);
+    if (rest == "input_layernorm.weight") return K_IN_NORM;
+    if (rest == "self_attn.q_proj.weight") return K_Q;
+    if (rest == "self_attn.k_proj.weight") return K_K;
+    if (rest == "self_attn.v_proj.weight") return K_V;
+    if (rest == "self_attn.o_proj.weight") return K_O;
+    if (rest == "post_attention_layernorm.weight") return K_POST_NORM;
+    if (rest == "mlp.gate_proj.weight") return K_GATE;
+    if (rest == "mlp.up_proj.weight") return K_UP;
+    if (rest == "mlp.down_proj.weight") return K_DOWN;
+    return K_BAD;
+}
+
+// where a (row, col) window of the full HF tensor lands in this rank's layout
+struct Placement {
+    uint16_t* dst;
+    int64_t dst_stride;  // elements between destination rows
+    int64_t row0, nrows, col0, ncols;
+    int64_t full_rows, full_cols;
+};
+
+template <typename T>
+T* dalloc(b2l_ctx* c, size_t n) {
+    void* p = nullptr;
+    B2L_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    c->allocs.push_back(p);
+    return static_cast<T*>(p);
+}
+
+Placement place_tensor(b2l_ctx* c, Kind k, int layer, const int64_t* shape, int ndim) {
+    const b2l_params& p = c->p;
+    const int64_t H = c->H, r = p.tp_rank;
+    const int64_t qd = static_cast<int64_t>(p.num_heads) * p.head_dim, kvd = static_cast<int64_t>(p.num_kv_heads) * p.head_dim;
+    auto want = [&](int64_t rows, int64_t cols) {
+        if (cols == 1 ? !(ndim == 1 && shape[0] == rows) : !(ndim == 2 && shape[0] == rows && shape[1] == cols))
+            throw Error("tensor shape mismatch");
+    };
+    if (k >= K_IN_NORM) B2L_CHECK(layer >= 0 && layer < c->L, "layer index out of range");
+    LayerWeights* lw = k >= K_IN_NORM ? &c->layers[layer] : nullptr;
+    switch (k) {
+        case K_EMBED: want(p.vocab_size, H); return {c->embed, H, 0, p.vocab_size, 0, H, p.vocab_size, H};
+        case K_LM_HEAD:
+            B2L_CHECK(!p.tie_word_embeddings, "lm_head.weight given for a tied model");
+            want(p.vocab_size, H);
+            return {c->lm_head, H, r * c->V_l, c->V_l, 0, H, p.vocab_size, H};
+        case K_FINAL_NORM: want(H, 1); return {c->final_norm, H, 0, 1, 0, H, 1, H};
+        case K_IN_NORM: want(H, 1); return {lw->in_norm, H, 0, 1, 0, H, 1, H};
+        case K_POST_NORM: want(H, 1); return {lw->post_norm, H, 0, 1, 0, H, 1, H};
+        case K_Q: want(qd, H); return {lw->w_qkv, H, r * c->qd_l, c->qd_l, 0, H, qd, H};
+        case K_K: want(kvd, H); return {lw->w_qkv + static_cast<int64_t>(c->qd_l) * H, H, r * c->kvd_l, c->kvd_l, 0, H, kvd, H};
+        case K_V: want(kvd, H); return {lw->w_qkv + static_cast<int64_t>(c->qd_l + c->kvd_l) * H, H, r * c->kvd_l, c->kvd_l, 0, H, kvd, H};
+        case K_O: want(H, qd); return {lw->w_o, c->qd_l, 0, H, r * c->qd_l, c->qd_l, H, qd};
+        case K_GATE: want(p.intermediate_size, H); return {lw->w_gu, 2 * H, r * c->I_l, c->I_l, 0, H, p.intermediate_size, H};
+        case K_UP: want(p.intermediate_size, H); return {lw->w_gu + H, 2 * H, r * c->I_l, c->I_l, 0, H, p.intermediate_size, H};
+        case K_DOWN: want(H, p.intermediate_size); return {lw->w_down, c->I_l, 0, H, r * c->I_l, c->I_l, H, p.intermediate_size};
+        default: throw Error("unknown tensor name");
+    }
+}
+
+void mark_tensor(b2l_ctx* c, Kind k, int layer) {
+    switch (k) {
+        case K_EMBED:
+            c->have_embed = true;
+            if (c->p.tie_word_embeddings) c->have_lm_head = true;
+            break;
+        case K_LM_HEAD: c->have_lm_head = true; break;
+        case K_FINAL_NORM: c->have_final_norm = true; break;
+        default: c->layers[layer].have |= 1u << k;
+    }
+}
+
+// ---- launches ----------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+void launch(b2l_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2L_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    c->launched++;
+}
+
+constexpr size_t kGemvSmemBudget = 96 * 1024;
+
+int gemv_kt(int B, int K) {
+    const int cap = static_cast<int>(kGemvSmemBudget / (4 * B)) / 256 * 256;
+    return std::min(K, cap);
+}
+
+template <int B, int MODE, bool NORM>
+void gemv_launch_b(b2l_ctx* c, const GemvArgs& a) {
+    static bool configured = false;
+    auto kern = gemv_kernel<B, MODE, NORM>;
+    if (!configured) {
+        B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemvSmemBudget)));
+        configured = true;
+    }
+    const int n_blocks = (a.N + kGemvRowsPerCta - 1) / kGemvRowsPerCta;
+    const int grid = std::min(n_blocks, c->prop.multiProcessorCount * 8);
+    launch(c, kern, dim3(grid), dim3(kGemvThreads), static_cast<size_t>(B) * a.kt * sizeof(float), a);
+}
+
+template <int MODE, bool NORM>
+void gemv_launch(b2l_ctx* c, GemvArgs a, int R) {
+    // rows in groups of <= 8; a group of 3 runs as 4 etc. (scratch buffers are sized in 8-row units)
+    for (int r0 = 0; r0 < R; r0 += 8) {
+        const int n = std::min(8, R - r0);
+        GemvArgs g = a;
+        g.x = a.x + static_cast<size_t>(r0) * a.ldx;
+        g.y = a.y + static_cast<size_t>(r0) * a.ldy;
+        const int B = n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : 8;
+        g.kt = gemv_kt(B, a.K);
+        switch (B) {
+            case 1: gemv_launch_b<1, MODE, NORM>(c, g); break;
+            case 2: gemv_launch_b<2, MODE, NORM>(c, g); break;
+            case 4: gemv_launch_b<4, MODE, NORM>(c, g); break;
+            default: gemv_launch_b<8, MODE, NORM>(c, g); break;
+        }
+    }
+}
+
+void gemv(b2l_ctx* c, const uint16_t* W, const float* x, int ldx, float* y, int ldy, const uint16_t* norm_w, int N,
+          int K, int mode, int R) {
+    B2L_CHECK(K % 8 == 0 && N % 2 == 0, "gemv: K must be a multiple of 8 and N even");
+    GemvArgs a{W, x, y, norm_w, nullptr, c->p.rms_norm_eps, N, K, ldx, ldy, 0};
+    if (norm_w) {
+        if (mode == 0) gemv_launch<0, true>(c, a, R);
+        else if (mode == 2) gemv_launch<2, true>(c, a, R);
+        else throw Error("gemv: unsupported fused-norm mode");
+    } else {
+        if (mode == 0) gemv_launch<0, false>(c, a, R);
+        else if (mode == 1) gemv_launch<1, false>(c, a, R);
+        else if (mode == 2) gemv_launch<2, false>(c, a, R);
+        else throw Error("gemv: bad mode");
+    }
+}
+
+template <int HD>
+void attn_launch_hd(b2l_ctx* c, const AttnArgs& a, int R) {
+    const dim3 grid(c->nsplit, c->nkv_l, R), block(kAttnThreads);
+    switch (c->group) {
+        case 1: launch(c, attn_decode_kernel<HD, 1>, grid, block, 0, a); break;
+        case 2: launch(c, attn_decode_kernel<HD, 2>, grid, block, 0, a); break;
+        case 3: launch(c, attn_decode_kernel<HD, 3>, grid, block, 0, a); break;
+        case 4: launch(c, attn_decode_kernel<HD, 4>, grid, block, 0, a); break;
+        case 8: launch(c, attn_decode_kernel<HD, 8>, grid, block, 0, a); break;
+        default: throw Error("unsupported GQA group size (heads per kv head must be 1,2,3,4 or 8)");
+    }
+}
+
+void attn_launch(b2l_ctx* c, const AttnArgs& a, int R) {
+    switch (c->hd) {
+        case 32: attn_launch_hd<32>(c, a, R); break;
+        case 64: attn_launch_hd<64>(c, a, R); break;
+        case 128: attn_launch_hd<128>(c, a, R); break;
+        default: throw Error("unsupported head_dim (32, 64 or 128)");
+    }
+}
+
+void tap_copy(b2l_ctx* c, int slab, int row0, const float* src, int R) {
+    float* dst = c->tap + (static_cast<size_t>(slab) * c->tap_rows_cap + row0) * c->H;
+    B2L_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * R * c->H, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+// The forward pass for R rows whose (token, position, slot) are already in device buffers.
+//   want_logits: run final norm + lm_head + argmax;  tap_row0 >= 0: record the residual stream.
+void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
+    const RowMeta rm{c->d_positions, c->d_slots, c->d_block_tables, c->max_blocks_cap};
+    launch(c, embed_kernel, dim3(R), dim3(256), 0, c->embed, c->d_tokens, c->h, c->H, c->V);
+    if (tap_row0 >= 0) tap_copy(c, 0, tap_row0, c->h, R);
+    const float scale = 1.0f / sqrtf(static_cast<float>(c->hd));
+    for (int l = 0; l < c->L; l++) {
+        const LayerWeights& w = c->layers[l];
+        const KvLayout kv{w.kv_pool, c->p.page_size, c->kvd_l};
+        gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
+        launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
+        const AttnArgs aa{c->qkv, c->qkv_l, kv, rm, c->part_acc, c->part_ml, c->attn_counters, c->attn, c->qd_l, scale};
+        attn_launch(c, aa, R);
+        gemv(c, w.w_o, c->attn, c->qd_l, c->h, c->H, nullptr, c->H, c->qd_l, 1, R);
+        gemv(c, w.w_gu, c->h, c->H, c->act, c->I_l, w.post_norm, 2 * c->I_l, c->H, 2, R);
+        gemv(c, w.w_down, c->act, c->I_l, c->h, c->H, nullptr, c->H, c->I_l, 1, R);
+        if (tap_row0 >= 0) tap_copy(c, l + 1, tap_row0, c->h, R);
+    }
+    if (tap_row0 >= 0) {
+        float* dst = c->tap + (static_cast<size_t>(c->L + 1) * c->tap_rows_cap + tap_row0) * c->H;
+        rmsnorm_kernel<<<R, 256, 0, c->stream>>>(c->h, c->final_norm, dst, c->H, c->p.rms_norm_eps);
+        c->launched++;
+    }
+    if (want_logits) {
+        gemv(c, c->lm_head, c->h, c->H, c->logits, c->V_l, c->final_norm, c->V_l, c->H, 0, R);
+        launch(c, argmax_kernel, dim3(R), dim3(1024), 0, static_cast<const float*>(c->logits), c->V_l, c->V_l,
+               c->p.tp_rank * c->V_l, c->d_next_ids, static_cast<float*>(nullptr));
+    }
+}
+
+Graph& decode_graph(b2l_ctx* c, int R, bool with_advance) {
+    const int key = R + (with_advance ? 1000 : 0);
+    auto it = c->decode_graphs.find(key);
+    if (it != c->decode_graphs.end()) return it->second;
+    Graph g;
+    const int64_t before = c->launched;
+    B2L_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        enqueue_forward(c, R, true, -1);
+        if (with_advance)
+            launch(c, advance_kernel, dim3(1), dim3(64), 0, static_cast<const int32_t*>(c->d_next_ids), c->d_tokens,
+                   c->d_positions, c->d_out_ids, c->d_step, R);
+    } catch (...) {
+        cudaGraph_t junk = nullptr;
+        cudaStreamEndCapture(c->stream, &junk);
+        if (junk) cudaGraphDestroy(junk);
+        throw;
+    }
+    B2L_CUDA(cudaStreamEndCapture(c->stream, &g.graph));
+    g.nodes = static_cast<int>(c->launched - before);
+    c->launched = before;  // capture is not execution
+    B2L_CUDA(cudaGraphInstantiate(&g.exec, g.graph, 0));
+    return c->decode_graphs.emplace(key, g).first->second;
+}
+
+void upload_rows_meta(b2l_ctx* c, int n_tok, const int32_t* tokens, const int32_t* positions, const int32_t* slots) {
+    // pinned staging -> async copies on the engine stream
+    int32_t* s = c->h_stage;
+    std::memcpy(s, tokens, sizeof(int32_t) * n_tok);
+    std::memcpy(s + c->max_rows, positions, sizeof(int32_t) * n_tok);
+    std::memcpy(s + 2 * c->max_rows, slots, sizeof(int32_t) * n_tok);
+    B2L_CUDA(cudaMemcpyAsync(c->d_tokens, s, sizeof(int32_t) * n_tok, cudaMemcpyHostToDevice, c->stream));
+    B2L_CUDA(cudaMemcpyAsync(c->d_positions, s + c->max_rows, sizeof(int32_t) * n_tok, cudaMemcpyHostToDevice, c->stream));
+    B2L_CUDA(cudaMemcpyAsync(c->d_slots, s + 2 * c->max_rows, sizeof(int32_t) * n_tok, cudaMemcpyHostToDevice, c->stream));
+}
+
+void upload_block_tables(b2l_ctx* c, int n_seq, const int32_t* bt, int max_blocks, const int32_t* need_tokens) {
+    B2L_CHECK(max_blocks >= 1, "max_blocks must be >= 1");
+    int32_t* s = c->h_stage + 3 * c->max_rows;
+    const int cap = c->max_blocks_cap;
+    for (int i = 0; i < n_seq; i++) {
+        const int need = (need_tokens[i] + c->p.page_size - 1) / c->p.page_size;
+        B2L_CHECK(need <= max_blocks && need <= cap, "block table too short for the sequence length");
+        for (int j = 0; j < cap; j++) {
+            const int32_t page = j < max_blocks ? bt[static_cast<size_t>(i) * max_blocks + j] : 0;
+            if (j < need) B2L_CHECK(page >= 0 && page < c->p.num_pages, "block table holds a page id outside the pool");
+            s[static_cast<size_t>(i) * cap + j] = j < need ? page : 0;
+        }
+    }
+    B2L_CUDA(cudaMemcpyAsync(c->d_block_tables, s, sizeof(int32_t) * n_seq * cap, cudaMemcpyHostToDevice, c->stream));
+}
+
+void require_ready(b2l_ctx* c) { B2L_CHECK(c->finalized, "b2l_finalize has not been called"); }
+
+template <typename F>
+int guarded(b2l_ctx* c, F&& f) {
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lock(c->mu);
+    try {
+        B2L_CUDA(cudaSetDevice(c->p.device));
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        c->err = e.what();
+        return 1;
+    }
+}
+
+// a throwaway mini-context (stream, events, allocation list) for the single-op entry points
+int op_guard(int device, const std::function<void(b2l_ctx*)>& f) {
+    b2l_ctx* c = nullptr;
+    try {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(std::string("no CUDA device (") + cudaGetErrorString(e) + "): the B200 path has no CPU fallback");
+        B2L_CHECK(device >= 0 && device < ndev, "device ordinal out of range");
+        B2L_CUDA(cudaSetDevice(device));
+        c = new b2l_ctx;
+        c->p.device = device;
+        B2L_CUDA(cudaGetDeviceProperties(&c->prop, device));
+        B2L_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        B2L_CUDA(cudaEventCreate(&c->ev0));
+        B2L_CUDA(cudaEventCreate(&c->ev1));
+        f(c);
+        b2l_destroy(c);
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        if (c) b2l_destroy(c);
+        return 1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2l_last_error(const b2l_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int b2l_nccl_unique_id(void* out_bytes) {
+    (void)out_bytes;
+    g_create_error = "tensor parallelism is not built into this library yet";
+    return 1;
+}
+
+int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_unique_id, b2l_ctx** out) {
+    b2l_ctx* c = nullptr;
+    try {
+        B2L_CHECK(p && out && rope_cos_sin, "null argument");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            throw Error(std::string("no CUDA device (") + cudaGetErrorString(e) + "): the B200 path has no CPU fallback");
+        B2L_CHECK(p->device >= 0 && p->device < ndev, "device ordinal out of range");
+        B2L_CHECK(p->tp_size >= 1 && p->tp_rank >= 0 && p->tp_rank < p->tp_size, "bad tp_rank / tp_size");
+        B2L_CHECK(p->tp_size == 1 || nccl_unique_id, "tp_size > 1 needs an NCCL unique id");
+        B2L_CHECK(p->tp_size == 1, "tensor parallelism is not built into this library yet");
+        B2L_CHECK(p->head_dim == 32 || p->head_dim == 64 || p->head_dim == 128, "head_dim must be 32, 64 or 128");
+        B2L_CHECK(p->num_heads % p->num_kv_heads == 0, "num_heads must be a multiple of num_kv_heads");
+        B2L_CHECK(p->num_kv_heads % p->tp_size == 0 && p->intermediate_size % p->tp_size == 0 && p->vocab_size % p->tp_size == 0,
+                  "kv heads, intermediate size and vocab must divide by tp_size");
+        B2L_CHECK(p->hidden_size % 256 == 0, "hidden_size must be a multiple of 256");
+        B2L_CHECK((p->intermediate_size / p->tp_size) % 8 == 0, "local intermediate size must be a multiple of 8");
+        B2L_CHECK(p->page_size == 16 || p->page_size == 32 || p->page_size == 64, "page_size must be 16, 32 or 64");
+        B2L_CHECK(p->max_batch >= 1 && p->max_batch <= 64, "max_batch must be in [1, 64]");
+        B2L_CHECK(p->num_pages >= 1 && p->max_positions >= 1 && p->max_prefill_tokens >= 1, "bad sizing");
+        B2L_CUDA(cudaSetDevice(p->device));
+        c = new b2l_ctx;
+        c->p = *p;
+        B2L_CUDA(cudaGetDeviceProperties(&c->prop, p->device));
+        B2L_CHECK(c->prop.major >= 10, "this library is built for sm_100a (B200) only");
+        B2L_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        B2L_CUDA(cudaEventCreate(&c->ev0));
+        B2L_CUDA(cudaEventCreate(&c->ev1));
+
+        const int tp = p->tp_size;
+        c->H = p->hidden_size; c->L = p->num_layers; c->hd = p->head_dim; c->V = p->vocab_size;
+        c->I_l = p->intermediate_size / tp; c->nh_l = p->num_heads / tp; c->nkv_l = p->num_kv_heads / tp;
+        c->V_l = p->vocab_size / tp;
+        c->qd_l = c->nh_l * c->hd; c->kvd_l = c->nkv_l * c->hd; c->qkv_l = c->qd_l + 2 * c->kvd_l;
+        c->group = p->num_heads / p->num_kv_heads;
+        c->max_rows = (std::max(p->max_batch, 8) + 7) / 8 * 8;
+        c->max_blocks_cap = (p->max_positions + p->page_size - 1) / p->page_size;
+        c->nsplit = std::max(1, std::min(32, (c->prop.multiProcessorCount + c->nkv_l - 1) / c->nkv_l));
+        if (c->nsplit > 16 && c->nkv_l >= 8) c->nsplit = 16;
+
+        // weights
+        const size_t H = c->H;
+        c->embed = dalloc<uint16_t>(c, static_cast<size_t>(c->V) * H);
+        c->weight_bytes += static_cast<int64_t>(c->V) * H * 2;
+        if (p->tie_word_embeddings) {
+            c->lm_head = c->embed + static_cast<size_t>(p->tp_rank) * c->V_l * H;
+        } else {
+            c->lm_head = dalloc<uint16_t>(c, static_cast<size_t>(c->V_l) * H);
+            c->weight_bytes += static_cast<int64_t>(c->V_l) * H * 2;
+        }
+        c->final_norm = dalloc<uint16_t>(c, H);
+        c->layers.resize(c->L);
+        const size_t page_elems = static_cast<size_t>(2) * p->page_size * c->kvd_l;
+        for (auto& w : c->layers) {
+            w.in_norm = dalloc<uint16_t>(c, H);
+            w.post_norm = dalloc<uint16_t>(c, H);
+            w.w_qkv = dalloc<uint16_t>(c, static_cast<size_t>(c->qkv_l) * H);
+            w.w_o = dalloc<uint16_t>(c, H * c->qd_l);
+            w.w_gu = dalloc<uint16_t>(c, static_cast<size_t>(2) * c->I_l * H);
+            w.w_down = dalloc<uint16_t>(c, H * c->I_l);
+            w.kv_pool = dalloc<uint16_t>(c, page_elems * p->num_pages);
+            c->weight_bytes += static_cast<int64_t>(2) * (2 * H + static_cast<size_t>(c->qkv_l) * H + H * c->qd_l + 3 * H * c->I_l);
+            c->kv_bytes += static_cast<int64_t>(2) * page_elems * p->num_pages;
+        }
+        c->weight_bytes += 2 * H;
+        c->rope = dalloc<float>(c, static_cast<size_t>(p->max_positions) * c->hd);
+        B2L_CUDA(cudaMemcpy(c->rope, rope_cos_sin, sizeof(float) * p->max_positions * c->hd, cudaMemcpyHostToDevice));
+
+        // per-call inputs
+        const int R = c->max_rows;
+        c->d_tokens = dalloc<int32_t>(c, R); c->d_positions = dalloc<int32_t>(c, R); c->d_slots = dalloc<int32_t>(c, R);
+        c->d_next_ids = dalloc<int32_t>(c, R); c->d_step = dalloc<int32_t>(c, 1);
+        c->d_block_tables = dalloc<int32_t>(c, static_cast<size_t>(p->max_batch) * c->max_blocks_cap);
+        c->h_stage_ints = 4 * static_cast<size_t>(R) + static_cast<size_t>(p->max_batch) * c->max_blocks_cap;
+        B2L_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_stage), c->h_stage_ints * sizeof(int32_t)));
+
+        // activations
+        c->h = dalloc<float>(c, static_cast<size_t>(R) * H);
+        c->qkv = dalloc<float>(c, static_cast<size_t>(R) * c->qkv_l);
+        c->attn = dalloc<float>(c, static_cast<size_t>(R) * c->qd_l);
+        c->act = dalloc<float>(c, static_cast<size_t>(R) * c->I_l);
+        c->proj = dalloc<float>(c, static_cast<size_t>(R) * H);
+        c->logits = dalloc<float>(c, static_cast<size_t>(R) * c->V_l);
+        c->seq_logits = dalloc<float>(c, static_cast<size_t>(p->max_batch) * c->V_l);
+        c->part_acc = dalloc<float>(c, static_cast<size_t>(R) * c->nkv_l * c->nsplit * c->group * c->hd);
+        c->part_ml = dalloc<float>(c, static_cast<size_t>(R) * c->nkv_l * c->nsplit * c->group * 2);
+        c->attn_counters = dalloc<int>(c, static_cast<size_t>(R) * c->nkv_l);
+        B2L_CUDA(cudaMemset(c->attn_counters, 0, sizeof(int) * R * c->nkv_l));
+        B2L_CUDA(cudaMemset(c->h, 0, sizeof(float) * R * H));
+        B2L_CUDA(cudaMemset(c->qkv, 0, sizeof(float) * R * c->qkv_l));
+        B2L_CUDA(cudaMemset(c->attn, 0, sizeof(float) * R * c->qd_l));
+        B2L_CUDA(cudaMemset(c->act, 0, sizeof(float) * R * c->I_l));
+        B2L_CUDA(cudaDeviceSynchronize());
+        *out = c;
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        if (c) b2l_destroy(c);
+        if (out) *out = nullptr;
+        return 1;
+    }
+}
+
+void b2l_destroy(b2l_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->p.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : c->decode_graphs) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int b2l_upload_tensor(b2l_ctx* c, const char* hf_name, const void* host_bf16, const int64_t* shape, int ndim) {
+    return guarded(c, [&] {
+        B2L_CHECK(hf_name && host_bf16 && shape, "null argument");
+        B2L_CHECK(!c->finalized, "tensors cannot change after b2l_finalize");
+        int layer;
+        const Kind k = parse_name(hf_name, &layer);
+        B2L_CHECK(k != K_BAD, std::string("unknown tensor name: ") + hf_name);
+        Placement pl;
+        try {
+            pl = place_tensor(c, k, layer, shape, ndim);
+        } catch (const Error& e) {
+            throw Error(std::string(hf_name) + ": " + e.what());
+        }
+        const uint16_t* src = static_cast<const uint16_t*>(host_bf16) + pl.row0 * pl.full_cols + pl.col0;
+        B2L_CUDA(cudaMemcpy2D(pl.dst, pl.dst_stride * 2, src, pl.full_cols * 2, pl.ncols * 2, pl.nrows, cudaMemcpyHostToDevice));
+        mark_tensor(c, k, layer);
+    });
+}
+
+int b2l_synth_tensor(b2l_ctx* c, const char* hf_name, const int64_t* shape, int ndim, uint32_t tensor_seed, float scale,
+                     float offset) {
+    return guarded(c, [&] {
+        B2L_CHECK(hf_name && shape, "null argument");
+        B2L_CHECK(!c->finalized, "tensors cannot change after b2l_finalize");
+        int layer;
+        const Kind k = parse_name(hf_name, &layer);
+        B2L_CHECK(k != K_BAD, std::string("unknown tensor name: ") + hf_name);
+        const Placement pl = place_tensor(c, k, layer, shape, ndim);
+        const int64_t n = pl.nrows * pl.ncols;
+        const int threads = 256;
+        const int blocks = static_cast<int>(std::min<int64_t>((n + threads - 1) / threads, 148 * 32));
+        synth_fill_kernel<<<blocks, threads, 0, c->stream>>>(pl.dst, pl.dst_stride, pl.row0, pl.nrows, pl.col0, pl.ncols,
+                                                             pl.full_cols, tensor_seed, scale, offset);
+        B2L_CUDA(cudaGetLastError());
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        mark_tensor(c, k, layer);
+    });
+}
+
+int b2l_finalize(b2l_ctx* c) {
+    return guarded(c, [&] {
+        B2L_CHECK(c->have_embed, "missing model.embed_tokens.weight");
+        B2L_CHECK(c->have_final_norm, "missing model.norm.weight");
+        B2L_CHECK(c->have_lm_head, "missing lm_head.weight (model is not tied)");
+        const uint32_t all = (1u << K_IN_NORM) | (1u << K_Q) | (1u << K_K) | (1u << K_V) | (1u << K_O) | (1u << K_POST_NORM) |
+                             (1u << K_GATE) | (1u << K_UP) | (1u << K_DOWN);
+        for (int l = 0; l < c->L; l++)
+            B2L_CHECK(c->layers[l].have == all, "layer " + std::to_string(l) + " is missing tensors");
+        B2L_CUDA(cudaDeviceSynchronize());
+        c->finalized = true;
+    });
+}
+
+int b2l_decode(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* positions, const int32_t* block_tables,
+               int max_blocks, int32_t* next_ids) {
+    return guarded(c, [&] {
+        require_ready(c);
+        B2L_CHECK(tokens && positions && block_tables && next_ids, "null argument");
+        B2L_CHECK(n_seq >= 1 && n_seq <= c->p.max_batch, "n_seq out of range");
+        std::vector<int32_t> slots(n_seq), need(n_seq);
+        for (int i = 0; i < n_seq; i++) {
+            B2L_CHECK(positions[i] >= 0 && positions[i] < c->p.max_positions, "position out of range");
+            B2L_CHECK(tokens[i] >= 0 && tokens[i] < c->V, "token id out of range");
+            slots[i] = i;
+            need[i] = positions[i] + 1;
+        }
+        upload_rows_meta(c, n_seq, tokens, positions, slots.data());
+        upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
+        if (c->taps) {
+            c->tap_rows = n_seq;
+            enqueue_forward(c, n_seq, true, 0);
+        } else {
+            Graph& g = decode_graph(c, n_seq, false);
+            B2L_CUDA(cudaGraphLaunch(g.exec, c->stream));
+            c->launched += g.nodes;
+        }
+        int32_t* h_next = c->h_stage + 3 * c->max_rows + static_cast<size_t>(c->p.max_batch) * c->max_blocks_cap;
+        B2L_CUDA(cudaMemcpyAsync(h_next, c->d_next_ids, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, c->stream));
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(next_ids, h_next, sizeof(int32_t) * n_seq);
+        c->logits_src = c->logits;
+        c->logits_rows = n_seq;
+    });
+}
+
+int b2l_decode_loop(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* positions, const int32_t* block_tables,
+                    int max_blocks, int n_steps, int32_t* out_ids, float* device_ms) {
+    return guarded(c, [&] {
+        require_ready(c);
+        B2L_CHECK(tokens && positions && block_tables && out_ids, "null argument");
+        B2L_CHECK(n_seq >= 1 && n_seq <= c->p.max_batch, "n_seq out of range");
+        B2L_CHECK(n_steps >= 1, "n_steps must be >= 1");
+        std::vector<int32_t> slots(n_seq), need(n_seq);
+        for (int i = 0; i < n_seq; i++) {
+            B2L_CHECK(positions[i] >= 0 && positions[i] + n_steps <= c->p.max_positions, "position + n_steps exceeds max_positions");
+            B2L_CHECK(tokens[i] >= 0 && tokens[i] < c->V, "token id out of range");
+            slots[i] = i;
+            need[i] = positions[i] + n_steps;
+        }
+        if (c->out_ids_cap < n_steps * n_seq) {
+            c->d_out_ids = dalloc<int32_t>(c, static_cast<size_t>(n_steps) * n_seq);
+            c->out_ids_cap = n_steps * n_seq;
+            // the captured advance kernel holds the old pointer
+            for (auto it = c->decode_graphs.begin(); it != c->decode_graphs.end();) {
+                if (it->first >= 1000) {
+                    cudaGraphExecDestroy(it->second.exec);
+                    cudaGraphDestroy(it->second.graph);
+                    it = c->decode_graphs.erase(it);
+                } else {
+                    ++it;
+                }
+            }
+        }
+        upload_rows_meta(c, n_seq, tokens, positions, slots.data());
+        upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
+        B2L_CUDA(cudaMemsetAsync(c->d_step, 0, sizeof(int32_t), c->stream));
+        Graph& g = decode_graph(c, n_seq, true);
+        B2L_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (int s = 0; s < n_steps; s++) B2L_CUDA(cudaGraphLaunch(g.exec, c->stream));
+        B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
+        c->launched += static_cast<int64_t>(g.nodes) * n_steps;
+        B2L_CUDA(cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        if (device_ms) B2L_CUDA(cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
+        c->logits_src = c->logits;
+        c->logits_rows = n_seq;
+    });
+}
+
+int b2l_prefill(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* q_lens, const int32_t* ctx_lens,
+                const int32_t* block_tables, int max_blocks, int32_t* next_ids) {
+    return guarded(c, [&] {
+        require_ready(c);
+        B2L_CHECK(tokens && q_lens && ctx_lens && block_tables && next_ids, "null argument");
+        B2L_CHECK(n_seq >= 1 && n_seq <= c->p.max_batch, "n_seq out of range");
+        std::vector<int32_t> need(n_seq);
+        int64_t total = 0;
+        for (int i = 0; i < n_seq; i++) {
+            B2L_CHECK(q_lens[i] >= 1 && ctx_lens[i] >= 0, "q_lens must be >= 1 and ctx_lens >= 0");
+            B2L_CHECK(ctx_lens[i] + q_lens[i] <= c->p.max_positions, "sequence exceeds max_positions");
+            need[i] = ctx_lens[i] + q_lens[i];
+            total += q_lens[i];
+        }
+        B2L_CHECK(total <= c->p.max_prefill_tokens, "prefill exceeds max_prefill_tokens");
+        for (int64_t i = 0; i < total; i++) B2L_CHECK(tokens[i] >= 0 && tokens[i] < c->V, "token id out of range");
+        if (c->taps) B2L_CHECK(total <= c->tap_rows_cap, "taps: prefill larger than the tap buffer");
+        upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
+        // Round-1 prefill: chunks of <= 8 consecutive positions through the decode kernels
+        // (each chunk appends its K/V before its attention runs, so causality holds inside it).
+        int64_t tok0 = 0;
+        for (int i = 0; i < n_seq; i++) {
+            for (int c0 = 0; c0 < q_lens[i]; c0 += 8) {
+                const int R = std::min(8, q_lens[i] - c0);
+                int32_t pos[8], slot[8];
+                for (int r = 0; r < R; r++) {
+                    pos[r] = ctx_lens[i] + c0 + r;
+                    slot[r] = i;
+                }
+                B2L_CUDA(cudaStreamSynchronize(c->stream));  // staging buffer reuse
+                upload_rows_meta(c, R, tokens + tok0 + c0, pos, slot);
+                const bool last = c0 + R >= q_lens[i];
+                enqueue_forward(c, R, last, c->taps ? static_cast<int>(tok0 + c0) : -1);
+                if (last)
+                    B2L_CUDA(cudaMemcpyAsync(c->seq_logits + static_cast<size_t>(i) * c->V_l,
+                                             c->logits + static_cast<size_t>(R - 1) * c->V_l, sizeof(float) * c->V_l,
+                                             cudaMemcpyDeviceToDevice, c->stream));
+            }
+            tok0 += q_lens[i];
+        }
+        launch(c, argmax_kernel, dim3(n_seq), dim3(1024), 0, static_cast<const float*>(c->seq_logits), c->V_l, c->V_l,
+               c->p.tp_rank * c->V_l, c->d_next_ids, static_cast<float*>(nullptr));
+        int32_t* h_next = c->h_stage + 3 * c->max_rows + static_cast<size_t>(c->p.max_batch) * c->max_blocks_cap;
+        B2L_CUDA(cudaMemcpyAsync(h_next, c->d_next_ids, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, c->stream));
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(next_ids, h_next, sizeof(int32_t) * n_seq);
+        c->logits_src = c->seq_logits;
+        c->logits_rows = n_seq;
+        c->tap_rows = static_cast<int>(total);
+    });
+}
+
+int b2l_get_logits(b2l_ctx* c, int row0, int n_rows, float* out) {
+    return guarded(c, [&] {
+        B2L_CHECK(out && c->logits_src, "no logits available (run prefill or decode first)");
+        B2L_CHECK(row0 >= 0 && n_rows >= 1 && row0 + n_rows <= c->logits_rows, "logit rows out of range");
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        B2L_CUDA(cudaMemcpy(out, c->logits_src + static_cast<size_t>(row0) * c->V_l, sizeof(float) * n_rows * c->V_l,
+                            cudaMemcpyDeviceToHost));
+    });
+}
+
+int b2l_set_taps(b2l_ctx* c, int enable) {
+    return guarded(c, [&] {
+        if (enable && !c->tap) {
+            c->tap_rows_cap = std::max(c->p.max_prefill_tokens, c->max_rows);
+            c->tap = dalloc<float>(c, static_cast<size_t>(c->L + 2) * c->tap_rows_cap * c->H);
+        }
+        c->taps = enable != 0;
+    });
+}
+
+int b2l_get_hidden(b2l_ctx* c, int slab, int row0, int n_rows, float* out) {
+    return guarded(c, [&] {
+        B2L_CHECK(out && c->tap, "taps are not enabled");
+        B2L_CHECK(slab >= 0 && slab <= c->L + 1, "slab out of range");
+        B2L_CHECK(row0 >= 0 && n_rows >= 1 && row0 + n_rows <= c->tap_rows, "rows out of range");
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        B2L_CUDA(cudaMemcpy(out, c->tap + (static_cast<size_t>(slab) * c->tap_rows_cap + row0) * c->H,
+                            sizeof(float) * n_rows * c->H, cudaMemcpyDeviceToHost));
+    });
+}
+
+int b2l_get_kv_page(b2l_ctx* c, int layer, int page, int which, void* out_bf16) {
+    return guarded(c, [&] {
+        B2L_CHECK(out_bf16 && layer >= 0 && layer < c->L && page >= 0 && page < c->p.num_pages && (which == 0 || which == 1),
+                  "bad kv page request");
+        const KvLayout kv{c->layers[layer].kv_pool, c->p.page_size, c->kvd_l};
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        B2L_CUDA(cudaMemcpy(out_bf16, c->layers[layer].kv_pool + ((static_cast<size_t>(page) * 2 + which) * c->p.page_size) * c->kvd_l,
+                            sizeof(uint16_t) * c->p.page_size * c->kvd_l, cudaMemcpyDeviceToHost));
+        (void)kv;
+    });
+}
+
+int b2l_get_info(b2l_ctx* c, b2l_info* out) {
+    return guarded(c, [&] {
+        B2L_CHECK(out, "null argument");
+        std::memset(out, 0, sizeof(*out));
+        out->abi_version = B2L_ABI_VERSION;
+        out->sm_count = c->prop.multiProcessorCount;
+        out->cc_major = c->prop.major;
+        out->cc_minor = c->prop.minor;
+        out->hbm_bytes = static_cast<int64_t>(c->prop.totalGlobalMem);
+        out->weight_bytes = c->weight_bytes;
+        out->kv_bytes = c->kv_bytes;
+        const int64_t H = c->H;
+        const int64_t per_layer = 2 * (2 * H + static_cast<int64_t>(c->qkv_l) * H + H * c->qd_l + 3 * H * c->I_l);
+        out->stream_bytes_per_token = per_layer * c->L + 2 * H + 2 * static_cast<int64_t>(c->V_l) * H + 2 * H;
+        out->kernels_launched = c->launched;
+        out->decode_mode = c->decode_mode;
+        std::snprintf(out->device_name, sizeof(out->device_name), "%s", c->prop.name);
+    });
+}
+
+int b2l_set_decode_mode(b2l_ctx* c, int mode) {
+    return guarded(c, [&] {
+        B2L_CHECK(mode == 0, "only decode mode 0 (multi-kernel graph) is built into this library yet");
+        c->decode_mode = mode;
+    });
+}
+
+// ---- single-op entry points ---------------------------------------------------------------
+
+int b2l_op_gemv(int device, const void* W_bf16, const float* x, float* y, const void* norm_w_bf16, float eps, int B, int N,
+                int K, int mode, int iters, float* device_ms) {
+    return op_guard(device, [&](b2l_ctx* c) {
+        B2L_CHECK(W_bf16 && x && y, "null argument");
+        B2L_CHECK(B >= 1 && B <= 64 && N >= 2 && K >= 8, "bad sizes");
+        B2L_CHECK(!(mode == 2 && (N % 2)), "SwiGLU mode needs an even N");
+        c->p.rms_norm_eps = eps;
+        const int out_cols = mode == 2 ? N / 2 : N;
+        const int Bp = (B + 7) / 8 * 8;
+        uint16_t* dW = dalloc<uint16_t>(c, static_cast<size_t>(N) * K);
+        uint16_t* dn = norm_w_bf16 ? dalloc<uint16_t>(c, K) : nullptr;
+        float* dx = dalloc<float>(c, static_cast<size_t>(Bp) * K);
+        float* dy = dalloc<float>(c, static_cast<size_t>(Bp) * out_cols);
+        float* dy0 = dalloc<float>(c, static_cast<size_t>(Bp) * out_cols);
+        B2L_CUDA(cudaMemset(dx, 0, sizeof(float) * Bp * K));
+        B2L_CUDA(cudaMemset(dy0, 0, sizeof(float) * Bp * out_cols));
+        B2L_CUDA(cudaMemcpy(dW, W_bf16, sizeof(uint16_t) * N * K, cudaMemcpyHostToDevice));
+        if (dn) B2L_CUDA(cudaMemcpy(dn, norm_w_bf16, sizeof(uint16_t) * K, cudaMemcpyHostToDevice));
+        B2L_CUDA(cudaMemcpy(dx, x, sizeof(float) * B * K, cudaMemcpyHostToDevice));
+        B2L_CUDA(cudaMemcpy(dy0, y, sizeof(float) * B * out_cols, cudaMemcpyHostToDevice));  // residual input (mode 1)
+        float total = 0.f;
+        for (int it = 0; it < std::max(1, iters); it++) {
+            B2L_CUDA(cudaMemcpyAsync(dy, dy0, sizeof(float) * Bp * out_cols, cudaMemcpyDeviceToDevice, c->stream));
+            B2L_CUDA(cudaEventRecord(c->ev0, c->stream));
+            gemv(c, dW, dx, K, dy, out_cols, dn, N, K, mode, B);
+            B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
+            B2L_CUDA(cudaStreamSynchronize(c->stream));
+            float ms;
+            B2L_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            if (it > 0 || iters <= 1) total += ms;
+        }
+        if (device_ms) *device_ms = total / std::max(1, iters > 1 ? iters - 1 : 1);
+        B2L_CUDA(cudaMemcpy(y, dy, sizeof(float) * B * out_cols, cudaMemcpyDeviceToHost));
+    });
+}
+
+int b2l_op_argmax(int device, const float* x, int B, int N, int32_t* out) {
+    return op_guard(device, [&](b2l_ctx* c) {
+        B2L_CHECK(x && out && B >= 1 && N >= 1, "bad argument");
+        float* dx = dalloc<float>(c, static_cast<size_t>(B) * N);
+        int32_t* di = dalloc<int32_t>(c, B);
+        B2L_CUDA(cudaMemcpy(dx, x, sizeof(float) * B * N, cudaMemcpyHostToDevice));
+        launch(c, argmax_kernel, dim3(B), dim3(1024), 0, static_cast<const float*>(dx), N, N, 0, di, static_cast<float*>(nullptr));
+        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        B2L_CUDA(cudaMemcpy(out, di, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+    });
+}
+
+}  // extern "C"
+

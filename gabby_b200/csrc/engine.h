@@ -1,0 +1,98 @@
+// engine.h -- device-side state behind the b2l C-ABI (include/b2l.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/b2l.h"
+
+namespace b2l {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define B2L_CUDA(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            throw ::b2l::Error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +    \
+                               std::to_string(__LINE__) + ")");                                            \
+    } while (0)
+
+#define B2L_CHECK(cond, msg)                      \
+    do {                                          \
+        if (!(cond)) throw ::b2l::Error(msg);     \
+    } while (0)
+
+struct LayerWeights {
+    uint16_t* in_norm = nullptr;    // [H]
+    uint16_t* w_qkv = nullptr;      // [(nh_l + 2 nkv_l) * hd][H]  rows: q heads, k heads, v heads
+    uint16_t* w_o = nullptr;        // [H][nh_l * hd]
+    uint16_t* post_norm = nullptr;  // [H]
+    uint16_t* w_gu = nullptr;       // [2 I_l][H]  row 2i = gate_i, 2i+1 = up_i
+    uint16_t* w_down = nullptr;     // [H][I_l]
+    uint16_t* kv_pool = nullptr;    // [num_pages][2][page_size][nkv_l * hd]
+    uint32_t have = 0;              // bit per HF tensor received
+};
+
+struct Graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int nodes = 0;
+};
+
+}  // namespace b2l
+
+struct b2l_ctx {
+    b2l_params p{};
+    std::mutex mu;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop{};
+    bool finalized = false;
+    int decode_mode = 0;
+    bool taps = false;
+
+    // local (per TP rank) dims
+    int H = 0, I_l = 0, nh_l = 0, nkv_l = 0, hd = 0, V = 0, V_l = 0, L = 0;
+    int qd_l = 0, kvd_l = 0, qkv_l = 0, group = 0;
+    int max_rows = 0, max_blocks_cap = 0, nsplit = 0;
+
+    // weights
+    uint16_t* embed = nullptr;       // [V][H] (replicated)
+    uint16_t* lm_head = nullptr;     // [V_l][H] (aliases embed + rank*V_l*H when tied)
+    uint16_t* final_norm = nullptr;  // [H]
+    bool have_embed = false, have_final_norm = false, have_lm_head = false;
+    std::vector<b2l::LayerWeights> layers;
+    float* rope = nullptr;           // [max_positions][hd/2][2]
+    int64_t weight_bytes = 0, kv_bytes = 0;
+
+    // per-call inputs (device) + pinned staging
+    int32_t *d_tokens = nullptr, *d_positions = nullptr, *d_slots = nullptr, *d_block_tables = nullptr;
+    int32_t *d_next_ids = nullptr, *d_out_ids = nullptr, *d_step = nullptr;
+    int32_t *h_stage = nullptr;      // pinned: tokens | positions | slots | block tables | next ids
+    size_t h_stage_ints = 0;
+    int out_ids_cap = 0;
+
+    // activations (fp32)
+    float *h = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *proj = nullptr, *logits = nullptr;
+    float *seq_logits = nullptr;     // [max_batch][V_l] (prefill keeps each sequence's last row here)
+    float *part_acc = nullptr, *part_ml = nullptr;
+    int* attn_counters = nullptr;
+    float* tap = nullptr;            // [(L+2)][tap_rows][H]
+    int tap_rows_cap = 0, tap_rows = 0;
+    const float* logits_src = nullptr;
+    int logits_rows = 0;
+
+    std::map<int, b2l::Graph> decode_graphs;  // key: rows (+ 1000 when the loop variant with advance)
+    int64_t launched = 0;
+
+    std::vector<void*> allocs;
+};
