@@ -13,6 +13,7 @@
 #include <functional>
 
 #include "decode_kernels.cuh"
+#include "mega_decode.cuh"
 #include "synth.cuh"
 
 using namespace b2l;
@@ -287,6 +288,123 @@ void upload_block_tables(b2l_ctx* c, int n_seq, const int32_t* bt, int max_block
     B2L_CUDA(cudaMemcpyAsync(c->d_block_tables, s, sizeof(int32_t) * n_seq * cap, cudaMemcpyHostToDevice, c->stream));
 }
 
+// ---- persistent megakernel (mega_decode.cuh) ------------------------------------------------
+bool mega_shape(int K, int* ks, int* m) {
+    for (int s = 1; s <= 8; s *= 2) {
+        if (K % (s * 256) == 0 && K / (s * 256) <= 8) {
+            *ks = s;
+            *m = K / (s * 256);
+            return true;
+        }
+    }
+    return false;
+}
+
+void mega_setup(b2l_ctx* c) {
+    c->mega_ok = false;
+    auto no = [&](const std::string& why) { c->mega_why = why; };
+    if (c->p.tp_size != 1) return no("tensor-parallel ranks use the multi-kernel path");
+    const int G = c->prop.multiProcessorCount;
+    std::vector<MegaPhase> ph;
+    auto add = [&](int type, int layer, const uint16_t* W, const uint16_t* norm, uint16_t* kv, int N, int K) -> bool {
+        MegaPhase p{};
+        p.type = type; p.layer = layer; p.W = W; p.norm_w = norm; p.kv_pool = kv; p.N = N; p.K = K; p.ks = 1; p.m = 1;
+        if (type != PH_ATTN && !mega_shape(K, &p.ks, &p.m)) return false;
+        if (type == PH_GATEUP && p.ks > 4) return false;
+        ph.push_back(p);
+        return true;
+    };
+    bool ok = true;
+    for (int l = 0; l < c->L && ok; l++) {
+        const LayerWeights& w = c->layers[l];
+        ok = ok && add(PH_QKV, l, w.w_qkv, w.in_norm, nullptr, c->qkv_l, c->H);
+        ok = ok && add(PH_ATTN, l, nullptr, nullptr, w.kv_pool, 0, 0);
+        ok = ok && add(PH_OPROJ, l, w.w_o, nullptr, nullptr, c->H, c->qd_l);
+        ok = ok && add(PH_GATEUP, l, w.w_gu, w.post_norm, nullptr, 2 * c->I_l, c->H);
+        ok = ok && add(PH_DOWN, l, w.w_down, nullptr, nullptr, c->H, c->I_l);
+    }
+    ok = ok && add(PH_LMHEAD, c->L, c->lm_head, c->final_norm, nullptr, c->V_l, c->H);
+    if (!ok) return no("a weight matrix has K that is not 256*m*ks with m<=8, ks in {1,2,4,8}");
+    if (c->nkv_l > G) return no("more kv heads than SMs");
+    c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
+    const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
+    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 128 + 64 + sizeof(float) * kMegaXsFloats + attn_scratch + 256;
+    int max_smem = 0;
+    B2L_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->p.device));
+    const int stages = std::min<int>(kMegaMaxStages, static_cast<int>((static_cast<size_t>(max_smem) - fixed) / kMegaStageBytes));
+    if (stages < 2) return no("not enough shared memory for the weight ring");
+    c->mega_stages = stages;
+    c->mega_smem = static_cast<size_t>(stages) * kMegaStageBytes + fixed;
+    B2L_CUDA(cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->mega_smem)));
+    int per_sm = 0;
+    B2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel, kMegaThreads, c->mega_smem));
+    if (per_sm < 1) return no("megakernel does not fit on an SM");
+    MegaPhase* d = dalloc<MegaPhase>(c, ph.size());
+    B2L_CUDA(cudaMemcpy(d, ph.data(), sizeof(MegaPhase) * ph.size(), cudaMemcpyHostToDevice));
+    c->mega_phases = d;
+    c->mega_n_phases = static_cast<int>(ph.size());
+    c->mega_bar = dalloc<unsigned long long>(c, 8);
+    B2L_CUDA(cudaMemset(c->mega_bar, 0, sizeof(unsigned long long) * 8));
+    B2L_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->mega_abort), sizeof(int), cudaHostAllocMapped));
+    *c->mega_abort = 0;
+    c->mega_ok = true;
+}
+
+// n_steps greedy tokens in one cooperative launch; token/position/block table already on the device
+void mega_enqueue(b2l_ctx* c, int n_steps) {
+    B2L_CHECK(c->mega_ok, "megakernel unavailable: " + c->mega_why);
+    MegaArgs a{};
+    a.phases = static_cast<const MegaPhase*>(c->mega_phases);
+    a.n_phases = c->mega_n_phases;
+    a.n_stages = c->mega_stages;
+    a.embed = c->embed; a.rope = c->rope;
+    a.H = c->H; a.V = c->V_l; a.nh = c->nh_l; a.nkv = c->nkv_l; a.hd = c->hd; a.I = c->I_l;
+    a.eps = c->p.rms_norm_eps; a.attn_scale = 1.0f / sqrtf(static_cast<float>(c->hd));
+    a.h = c->h; a.qkv = c->qkv; a.attn = c->attn; a.act = c->act; a.logits = c->logits;
+    a.block_table = c->d_block_tables; a.page_size = c->p.page_size; a.kvd = c->kvd_l;
+    a.part_acc = c->part_acc; a.part_ml = c->part_ml; a.attn_counters = c->attn_counters; a.nsplit_max = c->mega_nsplit;
+    a.token = c->d_tokens; a.position = c->d_positions; a.out_ids = c->d_out_ids; a.n_steps = n_steps;
+    a.bar_counter = c->mega_bar; a.bar_epoch = c->mega_bar + 1; a.argmax_keys = c->mega_bar + 2;
+    int* dev_abort = nullptr;
+    B2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_abort), c->mega_abort, 0));
+    a.abort_flag = dev_abort;
+    B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c->prop.multiProcessorCount);
+    cfg.blockDim = dim3(kMegaThreads);
+    cfg.dynamicSmemBytes = c->mega_smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel, a));
+    c->launched++;
+}
+
+void mega_check(b2l_ctx* c, cudaError_t sync_result) {
+    if (sync_result == cudaSuccess) return;
+    const int code = c->mega_abort ? *c->mega_abort : 0;
+    throw Error(std::string("megakernel failed: ") + cudaGetErrorString(sync_result) + " (abort code " + std::to_string(code) +
+                "; 100 = grid barrier timeout, 2xx = consumer wait, 3xx = producer wait)");
+}
+
+void ensure_out_ids(b2l_ctx* c, int n) {
+    if (c->out_ids_cap >= n) return;
+    c->d_out_ids = dalloc<int32_t>(c, static_cast<size_t>(n));
+    c->out_ids_cap = n;
+    for (auto it = c->decode_graphs.begin(); it != c->decode_graphs.end();) {  // captured advance kernels hold the old pointer
+        if (it->first >= 1000) {
+            cudaGraphExecDestroy(it->second.exec);
+            cudaGraphDestroy(it->second.graph);
+            it = c->decode_graphs.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
+
 void require_ready(b2l_ctx* c) { B2L_CHECK(c->finalized, "b2l_finalize has not been called"); }
 
 template <typename F>
@@ -455,6 +573,7 @@ void b2l_destroy(b2l_ctx* c) {
     }
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->mega_abort) cudaFreeHost(c->mega_abort);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -510,6 +629,9 @@ int b2l_finalize(b2l_ctx* c) {
         for (int l = 0; l < c->L; l++)
             B2L_CHECK(c->layers[l].have == all, "layer " + std::to_string(l) + " is missing tensors");
         B2L_CUDA(cudaDeviceSynchronize());
+        ensure_out_ids(c, 256);
+        mega_setup(c);
+        c->decode_mode = c->mega_ok ? 1 : 0;
         c->finalized = true;
     });
 }
@@ -529,9 +651,14 @@ int b2l_decode(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* posi
         }
         upload_rows_meta(c, n_seq, tokens, positions, slots.data());
         upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
+        bool mega = false;
         if (c->taps) {
             c->tap_rows = n_seq;
             enqueue_forward(c, n_seq, true, 0);
+        } else if (c->decode_mode == 1 && n_seq == 1) {
+            mega = true;
+            mega_enqueue(c, 1);
+            B2L_CUDA(cudaMemcpyAsync(c->d_next_ids, c->d_out_ids, sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
         } else {
             Graph& g = decode_graph(c, n_seq, false);
             B2L_CUDA(cudaGraphLaunch(g.exec, c->stream));
@@ -539,7 +666,8 @@ int b2l_decode(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* posi
         }
         int32_t* h_next = c->h_stage + 3 * c->max_rows + static_cast<size_t>(c->p.max_batch) * c->max_blocks_cap;
         B2L_CUDA(cudaMemcpyAsync(h_next, c->d_next_ids, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, c->stream));
-        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        if (mega) mega_check(c, cudaStreamSynchronize(c->stream));
+        else B2L_CUDA(cudaStreamSynchronize(c->stream));
         std::memcpy(next_ids, h_next, sizeof(int32_t) * n_seq);
         c->logits_src = c->logits;
         c->logits_rows = n_seq;
@@ -560,30 +688,25 @@ int b2l_decode_loop(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t*
             slots[i] = i;
             need[i] = positions[i] + n_steps;
         }
-        if (c->out_ids_cap < n_steps * n_seq) {
-            c->d_out_ids = dalloc<int32_t>(c, static_cast<size_t>(n_steps) * n_seq);
-            c->out_ids_cap = n_steps * n_seq;
-            // the captured advance kernel holds the old pointer
-            for (auto it = c->decode_graphs.begin(); it != c->decode_graphs.end();) {
-                if (it->first >= 1000) {
-                    cudaGraphExecDestroy(it->second.exec);
-                    cudaGraphDestroy(it->second.graph);
-                    it = c->decode_graphs.erase(it);
-                } else {
-                    ++it;
-                }
-            }
-        }
+        ensure_out_ids(c, n_steps * n_seq);
         upload_rows_meta(c, n_seq, tokens, positions, slots.data());
         upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
-        B2L_CUDA(cudaMemsetAsync(c->d_step, 0, sizeof(int32_t), c->stream));
-        Graph& g = decode_graph(c, n_seq, true);
-        B2L_CUDA(cudaEventRecord(c->ev0, c->stream));
-        for (int s = 0; s < n_steps; s++) B2L_CUDA(cudaGraphLaunch(g.exec, c->stream));
-        B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
-        c->launched += static_cast<int64_t>(g.nodes) * n_steps;
+        const bool mega = c->decode_mode == 1 && n_seq == 1;
+        if (mega) {
+            B2L_CUDA(cudaEventRecord(c->ev0, c->stream));
+            mega_enqueue(c, n_steps);
+            B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
+        } else {
+            B2L_CUDA(cudaMemsetAsync(c->d_step, 0, sizeof(int32_t), c->stream));
+            Graph& g = decode_graph(c, n_seq, true);
+            B2L_CUDA(cudaEventRecord(c->ev0, c->stream));
+            for (int s = 0; s < n_steps; s++) B2L_CUDA(cudaGraphLaunch(g.exec, c->stream));
+            B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
+            c->launched += static_cast<int64_t>(g.nodes) * n_steps;
+        }
         B2L_CUDA(cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
-        B2L_CUDA(cudaStreamSynchronize(c->stream));
+        if (mega) mega_check(c, cudaStreamSynchronize(c->stream));
+        else B2L_CUDA(cudaStreamSynchronize(c->stream));
         if (device_ms) B2L_CUDA(cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
         c->logits_src = c->logits;
         c->logits_rows = n_seq;
@@ -707,7 +830,9 @@ int b2l_get_info(b2l_ctx* c, b2l_info* out) {
 
 int b2l_set_decode_mode(b2l_ctx* c, int mode) {
     return guarded(c, [&] {
-        B2L_CHECK(mode == 0, "only decode mode 0 (multi-kernel graph) is built into this library yet");
+        B2L_CHECK(mode == 0 || mode == 1, "decode mode must be 0 (multi-kernel graph) or 1 (persistent megakernel)");
+        require_ready(c);
+        B2L_CHECK(mode == 0 || c->mega_ok, "megakernel unavailable: " + c->mega_why);
         c->decode_mode = mode;
     });
 }

@@ -91,6 +91,15 @@ struct b2l_ctx {
     const float* logits_src = nullptr;
     int logits_rows = 0;
 
+    // persistent megakernel (decode_mode 1, batch 1)
+    bool mega_ok = false;
+    std::string mega_why;            // why the megakernel is unavailable for this shape
+    void* mega_phases = nullptr;     // device MegaPhase[]
+    int mega_n_phases = 0, mega_stages = 0, mega_nsplit = 0;
+    size_t mega_smem = 0;
+    unsigned long long *mega_bar = nullptr;  // [0] counter, [1] epoch, [2..4] argmax keys
+    int* mega_abort = nullptr;               // pinned host flag, device-visible
+
     std::map<int, b2l::Graph> decode_graphs;  // key: rows (+ 1000 when the loop variant with advance)
     int64_t launched = 0;
 
