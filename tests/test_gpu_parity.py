@@ -260,3 +260,54 @@ def test_config1_llama32_1b_32_prompt_32_greedy_matches_cpu_oracle():
     oids, margins = om.seq(po.ORC_KV_BF16).greedy(prompt, 32)
     assert gpu_ids == oids.tolist(), f"min oracle top-1 margin {float(margins.min()):.4g}"
     assert len(set(gpu_ids)) > 4          # non-degenerate continuation
+
+
+# ---------------------------------------------------------------------------------------------
+# persistent megakernel (decode mode 1) against the multi-kernel path (mode 0) and the oracle
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("preset,layers,seed,n_prompt,n_new", [
+    ("tiny", None, 1234, 21, 24),        # hd 32, group 4, H 256 (m=1), I 512 (m=2)
+    ("tiny128", None, 77, 40, 100),      # hd 128, group 2, untied head; context crosses 64 and 128 (1 -> 2 -> 3 splits)
+    ("1b", 2, 5, 12, 8),                 # full 1B width: K 2048 (ks 1) and K 8192 (ks 4), V 128256
+])
+def test_megakernel_matches_multikernel_path_and_oracle(preset, layers, seed, n_prompt, n_new):
+    po = _po()
+    arch, tensors = synth_tensors(preset, layers, seed)
+    prompt = synth.synth_prompt(n_prompt, arch.vocab_size, arch.bos_token_id, seed + 3)
+    res = {}
+    for mode in (0, 1):
+        eng = make_engine(arch, tensors, max_positions=256)
+        assert eng.info().decode_mode == 1, "megakernel should be available for this shape"
+        eng.set_decode_mode(mode)
+        bt = contiguous_tables(1, eng.max_blocks)
+        first = eng.prefill([prompt], [0], bt)
+        ids, ms = eng.decode_loop(first, [n_prompt], bt, n_new)
+        # one more token through the per-step call, continuing from the loop's state
+        nxt = eng.decode([ids[-1, 0]], [n_prompt + n_new], bt)
+        res[mode] = (int(first[0]), ids[:, 0].tolist(), int(nxt[0]), eng.logits(0, 1)[0].copy(), eng.info().kernels_launched)
+        eng.close()
+    assert res[0][0] == res[1][0]
+    assert res[0][1] == res[1][1], "greedy ids differ between megakernel and multi-kernel path"
+    assert res[0][2] == res[1][2]
+    assert np.abs(res[0][3] - res[1][3]).max() < 2e-4
+    assert res[1][4] < res[0][4]          # far fewer launches
+    oids, margins = po.OracleModel(arch, tensors, 256).seq(po.ORC_KV_BF16).greedy(prompt, n_new + 2)
+    assert [res[1][0]] + res[1][1] + [res[1][2]] == oids.tolist(), f"min oracle margin {float(margins.min()):.3g}"
+
+
+def test_megakernel_relaunch_state_is_clean():
+    """Barrier epoch, argmax keys and split counters must carry over correctly between launches."""
+    arch, tensors = synth_tensors("tiny", None, 1234)
+    prompt = synth.synth_prompt(70, arch.vocab_size, arch.bos_token_id, 4)
+    eng = make_engine(arch, tensors, max_positions=256)
+    bt = contiguous_tables(1, eng.max_blocks)
+    first = eng.prefill([prompt], [0], bt)
+    a, _ = eng.decode_loop(first, [70], bt, 50)
+    b, _ = eng.decode_loop(first, [70], bt, 50)          # same start: identical continuation
+    assert a[:, 0].tolist() == b[:, 0].tolist()
+    ids, tok, pos = [], first, 70
+    for _ in range(50):                                  # 50 single-step launches
+        tok = eng.decode(tok, [pos], bt); pos += 1
+        ids.append(int(tok[0]))
+    assert ids == a[:, 0].tolist()
