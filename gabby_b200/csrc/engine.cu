@@ -368,6 +368,7 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     int* dev_abort = nullptr;
     B2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_abort), c->mega_abort, 0));
     a.abort_flag = dev_abort;
+    a.prof = c->mega_prof;
     B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->prop.multiProcessorCount);
@@ -825,6 +826,29 @@ int b2l_get_info(b2l_ctx* c, b2l_info* out) {
         out->kernels_launched = c->launched;
         out->decode_mode = c->decode_mode;
         std::snprintf(out->device_name, sizeof(out->device_name), "%s", c->prop.name);
+    });
+}
+
+int b2l_debug_mega_profile(b2l_ctx* c, int enable, uint64_t* out_ns, int* n_phases, int32_t* phase_types) {
+    return guarded(c, [&] {
+        require_ready(c);
+        B2L_CHECK(c->mega_ok, "megakernel unavailable: " + c->mega_why);
+        const size_t n = 4 * static_cast<size_t>(c->mega_n_phases + 1);
+        if (enable && !c->mega_prof) {
+            c->mega_prof = dalloc<unsigned long long>(c, n);
+            B2L_CUDA(cudaMemset(c->mega_prof, 0, n * 8));
+        }
+        if (n_phases) *n_phases = c->mega_n_phases;
+        if (out_ns && c->mega_prof) {
+            B2L_CUDA(cudaStreamSynchronize(c->stream));
+            B2L_CUDA(cudaMemcpy(out_ns, c->mega_prof, n * 8, cudaMemcpyDeviceToHost));
+        }
+        if (phase_types) {
+            std::vector<MegaPhase> ph(c->mega_n_phases);
+            B2L_CUDA(cudaMemcpy(ph.data(), c->mega_phases, sizeof(MegaPhase) * ph.size(), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < c->mega_n_phases; i++) phase_types[i] = ph[i].type;
+        }
+        if (!enable) c->mega_prof = nullptr;
     });
 }
 

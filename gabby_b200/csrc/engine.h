@@ -99,6 +99,7 @@ struct b2l_ctx {
     size_t mega_smem = 0;
     unsigned long long *mega_bar = nullptr;  // [0] counter, [1] epoch, [2..4] argmax keys
     int* mega_abort = nullptr;               // pinned host flag, device-visible
+    unsigned long long* mega_prof = nullptr; // device [4][n_phases+1] phase timestamps (debug)
 
     std::map<int, b2l::Graph> decode_graphs;  // key: rows (+ 1000 when the loop variant with advance)
     int64_t launched = 0;

@@ -66,7 +66,14 @@ struct MegaArgs {
     unsigned long long* bar_epoch;    // arrivals consumed by previous launches
     unsigned long long* argmax_keys;  // [3]
     int* abort_flag;
+    unsigned long long* prof;  // optional [4][n_phases + 1] globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---- PTX helpers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -74,20 +81,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
@@ -97,24 +104,42 @@ __device__ __noinline__ void mega_die(int* abort_flag, int code) {
     __threadfence_system();
     __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* abort_flag, int code) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag, int code) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) mega_die(abort_flag, code);
     }
 }
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kMegaConsumerThreads) : "memory"); }
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -134,57 +159,112 @@ __device__ __forceinline__ void mega_row_range(int N, int unit, int c, int G, in
 __device__ __forceinline__ void mega_grid_sync(const MegaArgs& a, unsigned long long target, int tid) {
     consumer_bar();  // all of this CTA's writes are ordered before thread 0's release below
     if (tid == 0) {
-        __threadfence();
-        atomicAdd(a.bar_counter, 1ull);
-        const long long t0 = clock64();
-        while (ld_acquire_u64(a.bar_counter) < target) {
-            if (clock64() - t0 > 4000000000ll) mega_die(a.abort_flag, 100);
+        // release: cumulative over the CTA's writes ordered by the bar.sync above; readers use ld.global.cg
+        red_release_add_u64(a.bar_counter, 1ull);
+        if (ld_acquire_u64(a.bar_counter) < target) {
+            const long long t0 = clock64();
+            while (ld_acquire_u64(a.bar_counter) < target) {
+                if (clock64() - t0 > 4000000000ll) mega_die(a.abort_flag, 100);
+            }
         }
-        __threadfence();
     }
     consumer_bar();
 }
 
-// ---- one GEMV-type phase for one CTA ---------------------------------------------------------
+// ---- shared memory map (32-bit shared-space addresses, kept in registers) ---------------------
 struct MegaSmem {
-    uint8_t* ring;       // [n_stages][kMegaStageBytes]
-    uint64_t* full;      // [n_stages]
-    uint64_t* empty;     // [n_stages]
-    float* xs;           // [kMegaXsFloats]
-    float* red;          // [32]
-    float* part;         // [2][8] per-chunk partial sums (double buffered)
-    unsigned long long* keys;  // [8]
-    float* attn_scratch;
+    uint32_t ring;          // [n_stages][kMegaStageBytes]
+    uint32_t full, empty;   // [n_stages] mbarriers each
+    uint32_t xs;            // [kMegaXsFloats] fp32
+    uint32_t red;           // [32] fp32
+    uint32_t part;          // [2][8] fp32 per-chunk partial sums (double buffered)
+    uint32_t keys;          // [8] u64
+    uint32_t attn_scratch;
+    float* gen;             // generic pointer to the same block's base (for the few generic accesses)
+    uint32_t base;
+    __device__ __forceinline__ float* generic(uint32_t addr) const {
+        return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(gen) + (addr - base));
+    }
 };
 
+// position in the ring: stage index and phase parity, advanced incrementally (no div/mod per chunk)
+struct RingPos {
+    int stage;
+    uint32_t parity;
+    int n_stages;
+    __device__ __forceinline__ void advance() {
+        if (++stage == n_stages) {
+            stage = 0;
+            parity ^= 1;
+        }
+    }
+};
+
+__device__ __forceinline__ int mega_nsplit(const MegaArgs& a, int ctx) { return max(1, min(a.nsplit_max, (ctx + 127) >> 7)); }
+
+// attention output element k (head-major) of this step: merge the split-K partials
+__device__ __forceinline__ void mega_attn_combine8(const MegaArgs& a, int k, int nsplit, float* out) {
+    const int head = k / a.hd, d = k % a.hd;  // 8 consecutive k never straddle a head (hd % 8 == 0)
+    const int group = a.nh / a.nkv, kvh = head / group, g = head % group;
+    const size_t rbase = static_cast<size_t>(kvh) * a.nsplit_max;
+    float M = -INFINITY;
+    for (int s = 0; s < nsplit; s++) M = fmaxf(M, __ldcg(a.part_ml + ((rbase + s) * group + g) * 2));
+    float L = 0.f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int s = 0; s < nsplit; s++) {
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(a.part_ml + ((rbase + s) * group + g) * 2));
+        if (ml.x == -INFINITY) continue;
+        const float wgt = __expf(ml.x - M);
+        L = fmaf(ml.y, wgt, L);
+        const float* pa = a.part_acc + ((rbase + s) * group + g) * a.hd + d;
+        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(pa)), p1 = __ldcg(reinterpret_cast<const float4*>(pa + 4));
+        acc[0] = fmaf(p0.x, wgt, acc[0]); acc[1] = fmaf(p0.y, wgt, acc[1]); acc[2] = fmaf(p0.z, wgt, acc[2]); acc[3] = fmaf(p0.w, wgt, acc[3]);
+        acc[4] = fmaf(p1.x, wgt, acc[4]); acc[5] = fmaf(p1.y, wgt, acc[5]); acc[6] = fmaf(p1.z, wgt, acc[6]); acc[7] = fmaf(p1.w, wgt, acc[7]);
+    }
+    const float inv = 1.0f / L;
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = acc[i] * inv;
+}
+
+// ---- one GEMV-type phase for one CTA ---------------------------------------------------------
 template <int M>
-__device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase& ph, const MegaSmem& sm, uint32_t& cc,
-                                             int token, unsigned long long& best_key, int tid) {
+__device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase& ph, const MegaSmem sm, RingPos& rp, int token,
+                                             int pos, unsigned long long& best_key, int tid) {
     const int lane = tid & 31, w = tid >> 5;
     const int ks = ph.ks, RC = 8 / ks, slice = 256 * M;
     const int q = w % ks, rloc = w / ks;
-    const int K = ph.K;
-    // ---- input vector -> registers (fused RMSNorm) ----
-    const float* xsrc = ph.type == PH_OPROJ ? a.attn : ph.type == PH_DOWN ? a.act : a.h;
-    const bool from_embed = (ph.type == PH_QKV && ph.layer == 0);
+    const int K = ph.K, type = ph.type;
+    // ---- input vector -> registers (fused RMSNorm / split-K attention merge) ----
+    const float* xsrc = type == PH_DOWN ? a.act : a.h;
+    const bool from_embed = (type == PH_QKV && ph.layer == 0);
+    const int nsplit = mega_nsplit(a, pos + 1);
     float xr[M * 8];
     if (ks == 1) {
         // every warp needs the same K floats: fetch once per CTA, then fan out through smem
-        for (int k = tid * 4; k < K; k += kMegaConsumerThreads * 4) {
-            float4 v;
-            if (from_embed) {
-                const uint2 e = *reinterpret_cast<const uint2*>(a.embed + static_cast<size_t>(token) * a.H + k);
-                v = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
-            } else {
-                v = __ldcg(reinterpret_cast<const float4*>(xsrc + k));
+        if (type == PH_OPROJ) {
+            for (int k = tid * 8; k < K; k += kMegaConsumerThreads * 8) {
+                float v[8];
+                mega_attn_combine8(a, k, nsplit, v);
+                sts128f(sm.xs + k * 4, make_float4(v[0], v[1], v[2], v[3]));
+                sts128f(sm.xs + k * 4 + 16, make_float4(v[4], v[5], v[6], v[7]));
             }
-            *reinterpret_cast<float4*>(sm.xs + k) = v;
+        } else {
+            for (int k = tid * 4; k < K; k += kMegaConsumerThreads * 4) {
+                float4 v;
+                if (from_embed) {
+                    const uint2 e = *reinterpret_cast<const uint2*>(a.embed + static_cast<size_t>(token) * a.H + k);
+                    v = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
+                } else {
+                    v = __ldcg(reinterpret_cast<const float4*>(xsrc + k));
+                }
+                sts128f(sm.xs + k * 4, v);
+            }
         }
         consumer_bar();
 #pragma unroll
         for (int i = 0; i < M; i++) {
-            const float4 v0 = *reinterpret_cast<const float4*>(sm.xs + i * 256 + lane * 8);
-            const float4 v1 = *reinterpret_cast<const float4*>(sm.xs + i * 256 + lane * 8 + 4);
+            const float4 v0 = lds128f(sm.xs + (i * 256 + lane * 8) * 4), v1 = lds128f(sm.xs + (i * 256 + lane * 8) * 4 + 16);
             xr[i * 8 + 0] = v0.x; xr[i * 8 + 1] = v0.y; xr[i * 8 + 2] = v0.z; xr[i * 8 + 3] = v0.w;
             xr[i * 8 + 4] = v1.x; xr[i * 8 + 5] = v1.y; xr[i * 8 + 6] = v1.z; xr[i * 8 + 7] = v1.w;
         }
@@ -192,6 +272,10 @@ __device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase&
 #pragma unroll
         for (int i = 0; i < M; i++) {
             const int k = q * slice + i * 256 + lane * 8;
+            if (type == PH_OPROJ) {
+                mega_attn_combine8(a, k, nsplit, &xr[i * 8]);
+                continue;
+            }
             float4 v0, v1;
             if (from_embed) {
                 const uint4 e = *reinterpret_cast<const uint4*>(a.embed + static_cast<size_t>(token) * a.H + k);
@@ -206,76 +290,90 @@ __device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase&
         }
     }
     if (ph.norm_w) {
+        uint4 nw[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) nw[i] = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + q * slice + i * 256 + lane * 8));
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < M * 8; i++) ss = fmaf(xr[i], xr[i], ss);
         ss = warp_sum(ss);
-        if (lane == 0) sm.red[w] = ss;
+        float* red = sm.generic(sm.red);
+        if (lane == 0) red[w] = ss;
         consumer_bar();
         float tot = 0.f;
-        for (int i = 0; i < ks; i++) tot += sm.red[i];  // warps 0..ks-1 hold slices 0..ks-1
+        for (int i = 0; i < ks; i++) tot += red[i];  // warps 0..ks-1 hold slices 0..ks-1
         const float inv = rsqrtf(tot / static_cast<float>(K) + a.eps);
 #pragma unroll
         for (int i = 0; i < M; i++) {
-            const uint4 nw = *reinterpret_cast<const uint4*>(ph.norm_w + q * slice + i * 256 + lane * 8);
-            xr[i * 8 + 0] = bf16lo(nw.x) * (xr[i * 8 + 0] * inv);
-            xr[i * 8 + 1] = bf16hi(nw.x) * (xr[i * 8 + 1] * inv);
-            xr[i * 8 + 2] = bf16lo(nw.y) * (xr[i * 8 + 2] * inv);
-            xr[i * 8 + 3] = bf16hi(nw.y) * (xr[i * 8 + 3] * inv);
-            xr[i * 8 + 4] = bf16lo(nw.z) * (xr[i * 8 + 4] * inv);
-            xr[i * 8 + 5] = bf16hi(nw.z) * (xr[i * 8 + 5] * inv);
-            xr[i * 8 + 6] = bf16lo(nw.w) * (xr[i * 8 + 6] * inv);
-            xr[i * 8 + 7] = bf16hi(nw.w) * (xr[i * 8 + 7] * inv);
+            xr[i * 8 + 0] = bf16lo(nw[i].x) * (xr[i * 8 + 0] * inv);
+            xr[i * 8 + 1] = bf16hi(nw[i].x) * (xr[i * 8 + 1] * inv);
+            xr[i * 8 + 2] = bf16lo(nw[i].y) * (xr[i * 8 + 2] * inv);
+            xr[i * 8 + 3] = bf16hi(nw[i].y) * (xr[i * 8 + 3] * inv);
+            xr[i * 8 + 4] = bf16lo(nw[i].z) * (xr[i * 8 + 4] * inv);
+            xr[i * 8 + 5] = bf16hi(nw[i].z) * (xr[i * 8 + 5] * inv);
+            xr[i * 8 + 6] = bf16lo(nw[i].w) * (xr[i * 8 + 6] * inv);
+            xr[i * 8 + 7] = bf16hi(nw[i].w) * (xr[i * 8 + 7] * inv);
         }
     }
 
     // ---- stream this CTA's rows ----
     int r0, r1;
-    mega_row_range(ph.N, ph.type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
+    mega_row_range(ph.N, type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
     const int n_chunks = (r1 - r0 + RC - 1) / RC;
-    const bool cross = (ks > 1) || ph.type == PH_GATEUP;  // result needs more than one warp
-    for (int ch = 0; ch < n_chunks; ch++, cc++) {
-        const int stage = cc % a.n_stages;
-        const uint32_t parity = (cc / a.n_stages) & 1;
+    const bool cross = (ks > 1) || type == PH_GATEUP;  // result needs more than one warp
+    const uint32_t unit_off = (static_cast<uint32_t>(rloc) * K + static_cast<uint32_t>(q) * slice) * 2 + lane * 16;
+    float* part_base = sm.generic(sm.part);
+    for (int ch = 0; ch < n_chunks; ch++) {
         const int row = r0 + ch * RC + rloc;
         const bool valid = row < r1;
-        mbar_wait(&sm.full[stage], parity, a.abort_flag, 200 + ph.type);
-        float acc0 = 0.f, acc1 = 0.f;
+        mbar_wait(sm.full + rp.stage * 8, rp.parity, a.abort_flag, 200 + type);
+        float acc[M];
         if (valid) {
-            const uint8_t* base = sm.ring + static_cast<size_t>(stage) * kMegaStageBytes +
-                                  (static_cast<size_t>(rloc) * K + static_cast<size_t>(q) * slice) * 2 + lane * 16;
+            const uint32_t base = sm.ring + static_cast<uint32_t>(rp.stage) * kMegaStageBytes + unit_off;
+            uint4 wv[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) wv[i] = lds128(base + i * 512);
 #pragma unroll
             for (int i = 0; i < M; i++) {
-                const uint4 wv = *reinterpret_cast<const uint4*>(base + i * 512);
-                float& acc = (i & 1) ? acc1 : acc0;
-                acc = fmaf(bf16lo(wv.x), xr[i * 8 + 0], acc);
-                acc = fmaf(bf16hi(wv.x), xr[i * 8 + 1], acc);
-                acc = fmaf(bf16lo(wv.y), xr[i * 8 + 2], acc);
-                acc = fmaf(bf16hi(wv.y), xr[i * 8 + 3], acc);
-                acc = fmaf(bf16lo(wv.z), xr[i * 8 + 4], acc);
-                acc = fmaf(bf16hi(wv.z), xr[i * 8 + 5], acc);
-                acc = fmaf(bf16lo(wv.w), xr[i * 8 + 6], acc);
-                acc = fmaf(bf16hi(wv.w), xr[i * 8 + 7], acc);
+                float s = bf16lo(wv[i].x) * xr[i * 8 + 0];
+                s = fmaf(bf16hi(wv[i].x), xr[i * 8 + 1], s);
+                s = fmaf(bf16lo(wv[i].y), xr[i * 8 + 2], s);
+                s = fmaf(bf16hi(wv[i].y), xr[i * 8 + 3], s);
+                s = fmaf(bf16lo(wv[i].z), xr[i * 8 + 4], s);
+                s = fmaf(bf16hi(wv[i].z), xr[i * 8 + 5], s);
+                s = fmaf(bf16lo(wv[i].w), xr[i * 8 + 6], s);
+                s = fmaf(bf16hi(wv[i].w), xr[i * 8 + 7], s);
+                acc[i] = s;
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < M; i++) acc[i] = 0.f;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);  // smem slot can be refilled
-        float s = warp_sum(acc0 + acc1);
+        if (lane == 0) mbar_arrive(sm.empty + rp.stage * 8);  // smem slot can be refilled
+        rp.advance();
+        // tree-add the M sweep sums, then across lanes
+#pragma unroll
+        for (int st = 1; st < M; st <<= 1) {
+#pragma unroll
+            for (int i = 0; i + st < M; i += 2 * st) acc[i] += acc[i + st];
+        }
+        float s = warp_sum(acc[0]);
         if (cross) {
-            float* part = sm.part + (ch & 1) * 8;
+            float* part = part_base + (ch & 1) * 8;
             if (lane == 0) part[w] = s;
             consumer_bar();
-            if (q != 0 || (ph.type == PH_GATEUP && (rloc & 1))) continue;  // one finalising warp per row / pair
+            if (q != 0 || (type == PH_GATEUP && (rloc & 1))) continue;  // one finalising warp per row / pair
             s = 0.f;
             for (int i = 0; i < ks; i++) s += part[w + i];
-            if (ph.type == PH_GATEUP) {
+            if (type == PH_GATEUP) {
                 float u = 0.f;
                 for (int i = 0; i < ks; i++) u += part[w + ks + i];
-                s = (s / (1.0f + __expf(-s))) * u;   // silu(gate) * up
+                s = (s / (1.0f + __expf(-s))) * u;  // silu(gate) * up
             }
         }
         if (lane == 0 && valid) {
-            switch (ph.type) {
+            switch (type) {
                 case PH_QKV: a.qkv[row] = s; break;
                 case PH_GATEUP: a.act[row >> 1] = s; break;
                 case PH_OPROJ:
@@ -295,10 +393,10 @@ __device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase&
     }
 }
 
-// ---- attention work item: (kv head, split) ------------------------------------------------------
+// ---- attention work item: (kv head, split); partials are merged by the O-proj phase's x load -----
 template <int HD, int GROUP>
-__device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& ph, const MegaSmem& sm, int kvh, int split, int nsplit,
-                               int pos, int tid) {
+__device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& ph, const MegaSmem sm, int kvh, int split,
+                                            int nsplit, int pos, int tid) {
     constexpr int LPT = HD / 8, TPW = 32 / LPT, HALF = HD / 2;
     const int lane = tid & 31, w = tid >> 5, sub = lane / LPT, sl = lane % LPT;
     const KvLayout kv{ph.kv_pool, a.page_size, a.kvd};
@@ -310,13 +408,16 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
 
     // rotate-half RoPE of one 8-wide slice of a head living in the fused qkv row
     auto rope_slice = [&](const float* head, float* out) {
+        const int d0 = sl * 8, j0r = d0 < HALF ? d0 : d0 - HALF;  // the slice lies in one half (HALF % 8 == 0)
+        const float4 xa0 = __ldcg(reinterpret_cast<const float4*>(head + j0r)), xa1 = __ldcg(reinterpret_cast<const float4*>(head + j0r + 4));
+        const float4 xb0 = __ldcg(reinterpret_cast<const float4*>(head + j0r + HALF)), xb1 = __ldcg(reinterpret_cast<const float4*>(head + j0r + HALF + 4));
+        const float x0[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
+        const float x1[8] = {xb0.x, xb0.y, xb0.z, xb0.w, xb1.x, xb1.y, xb1.z, xb1.w};
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int d = sl * 8 + i;
-            const int j = d < HALF ? d : d - HALF;
-            const float c = cs[2 * j], s = cs[2 * j + 1];
-            const float x0 = __ldcg(head + j), x1 = __ldcg(head + j + HALF);
-            out[i] = d < HALF ? x0 * c - x1 * s : x1 * c + x0 * s;
+        for (int i = 0; i < 8; i += 2) {
+            const float4 c2 = __ldg(reinterpret_cast<const float4*>(cs + 2 * (j0r + i)));  // (c, s, c', s')
+            out[i] = d0 < HALF ? x0[i] * c2.x - x1[i] * c2.y : x1[i] * c2.x + x0[i] * c2.y;
+            out[i + 1] = d0 < HALF ? x0[i + 1] * c2.z - x1[i + 1] * c2.w : x1[i + 1] * c2.z + x0[i + 1] * c2.w;
         }
     };
     float q[GROUP][8];
@@ -337,14 +438,11 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
     for (int jb = j0; jb < j1; jb += kMegaConsumerWarps * TPW) {
         const int j = jb + w * TPW + sub;
         const bool valid = j < j1;
-        float kf[8], vf[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) kf[i] = vf[i] = 0.f;
+        uint4 kw = make_uint4(0, 0, 0, 0), vw = make_uint4(0, 0, 0, 0);
         if (valid) {
-            const int page = a.block_table[j / a.page_size], off = j % a.page_size;
+            const int page = __ldg(a.block_table + j / a.page_size), off = j % a.page_size;
             uint16_t* kp = kv.at(page, 0, off) + kvh * HD + sl * 8;
             uint16_t* vp = kv.at(page, 1, off) + kvh * HD + sl * 8;
-            uint4 kw, vw;
             if (j == pos) {
                 // the token being decoded: K/V come from this step's projection; append them (bf16)
                 float kr[8];
@@ -359,11 +457,9 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
                 kw = __ldcg(reinterpret_cast<const uint4*>(kp));
                 vw = __ldcg(reinterpret_cast<const uint4*>(vp));
             }
-            kf[0] = bf16lo(kw.x); kf[1] = bf16hi(kw.x); kf[2] = bf16lo(kw.y); kf[3] = bf16hi(kw.y);
-            kf[4] = bf16lo(kw.z); kf[5] = bf16hi(kw.z); kf[6] = bf16lo(kw.w); kf[7] = bf16hi(kw.w);
-            vf[0] = bf16lo(vw.x); vf[1] = bf16hi(vw.x); vf[2] = bf16lo(vw.y); vf[3] = bf16hi(vw.y);
-            vf[4] = bf16lo(vw.z); vf[5] = bf16hi(vw.z); vf[6] = bf16lo(vw.w); vf[7] = bf16hi(vw.w);
         }
+        const float kf[8] = {bf16lo(kw.x), bf16hi(kw.x), bf16lo(kw.y), bf16hi(kw.y), bf16lo(kw.z), bf16hi(kw.z), bf16lo(kw.w), bf16hi(kw.w)};
+        const float vf[8] = {bf16lo(vw.x), bf16hi(vw.x), bf16lo(vw.y), bf16hi(vw.y), bf16lo(vw.z), bf16hi(vw.z), bf16lo(vw.w), bf16hi(vw.w)};
 #pragma unroll
         for (int g = 0; g < GROUP; g++) {
             float s = 0.f;
@@ -399,8 +495,8 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
         }
     }
     // per-warp results -> smem: [w][g][HD] then (m, l)
-    float* s_acc = sm.attn_scratch;                                   // [8][GROUP][HD]
-    float* s_ml = sm.attn_scratch + kMegaConsumerWarps * GROUP * HD;  // [8][GROUP][2]
+    float* s_acc = sm.generic(sm.attn_scratch);               // [8][GROUP][HD]
+    float* s_ml = s_acc + kMegaConsumerWarps * GROUP * HD;    // [8][GROUP][2]
     if (sub == 0) {
 #pragma unroll
         for (int g = 0; g < GROUP; g++) {
@@ -416,55 +512,23 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
     const size_t pbase = static_cast<size_t>(kvh) * a.nsplit_max + split;
     for (int e = tid; e < GROUP * HD; e += kMegaConsumerThreads) {
         const int g = e / HD, d = e % HD;
-        float M = -INFINITY;
+        float Mx = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < kMegaConsumerWarps; t++) M = fmaxf(M, s_ml[(t * GROUP + g) * 2]);
+        for (int t = 0; t < kMegaConsumerWarps; t++) Mx = fmaxf(Mx, s_ml[(t * GROUP + g) * 2]);
         float L = 0.f, A = 0.f;
-        if (M > -INFINITY) {
+        if (Mx > -INFINITY) {
 #pragma unroll
             for (int t = 0; t < kMegaConsumerWarps; t++) {
-                const float wgt = __expf(s_ml[(t * GROUP + g) * 2] - M);
+                const float wgt = __expf(s_ml[(t * GROUP + g) * 2] - Mx);
                 L = fmaf(s_ml[(t * GROUP + g) * 2 + 1], wgt, L);
                 A = fmaf(s_acc[(t * GROUP + g) * HD + d], wgt, A);
             }
         }
-        if (nsplit == 1) {
-            a.attn[(kvh * GROUP + g) * HD + d] = A / L;
-        } else {
-            a.part_acc[(pbase * GROUP + g) * HD + d] = A;
-            if (d == 0) {
-                a.part_ml[(pbase * GROUP + g) * 2] = M;
-                a.part_ml[(pbase * GROUP + g) * 2 + 1] = L;
-            }
+        a.part_acc[(pbase * GROUP + g) * HD + d] = A;
+        if (d == 0) {
+            a.part_ml[(pbase * GROUP + g) * 2] = Mx;
+            a.part_ml[(pbase * GROUP + g) * 2 + 1] = L;
         }
-    }
-    if (nsplit == 1) return;
-    // last-arriving split of this kv head merges them
-    __threadfence();
-    consumer_bar();
-    int* s_flag = reinterpret_cast<int*>(sm.red + 16);
-    if (tid == 0) {
-        const int done = atomicAdd(a.attn_counters + kvh, 1);
-        *s_flag = (done == nsplit - 1);
-        if (done == nsplit - 1) a.attn_counters[kvh] = 0;
-    }
-    consumer_bar();
-    if (!*s_flag) return;
-    __threadfence();
-    const size_t rbase = static_cast<size_t>(kvh) * a.nsplit_max;
-    for (int e = tid; e < GROUP * HD; e += kMegaConsumerThreads) {
-        const int g = e / HD, d = e % HD;
-        float M = -INFINITY;
-        for (int s = 0; s < nsplit; s++) M = fmaxf(M, __ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2));
-        float L = 0.f, A = 0.f;
-        for (int s = 0; s < nsplit; s++) {
-            const float ms = __ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2);
-            if (ms == -INFINITY) continue;
-            const float wgt = __expf(ms - M);
-            L = fmaf(__ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2 + 1), wgt, L);
-            A = fmaf(__ldcg(a.part_acc + ((rbase + s) * GROUP + g) * HD + d), wgt, A);
-        }
-        a.attn[(kvh * GROUP + g) * HD + d] = A / L;
     }
 }
 
@@ -480,24 +544,69 @@ __device__ __forceinline__ void mega_attn_group(const MegaArgs& a, const MegaPha
     }
 }
 
+// the producer's view of the weight stream: every chunk this CTA needs, in model order, forever
+struct ChunkCursor {
+    int step, pi, row, r1, RC;
+    long long index;
+    __device__ __forceinline__ bool done(const MegaArgs& a) const { return step >= a.n_steps; }
+    __device__ __forceinline__ void seek_phase(const MegaArgs& a, int G) {
+        // move to the first row of the next phase that has weights and rows for this CTA
+        for (;;) {
+            if (pi >= a.n_phases) {
+                pi = 0;
+                step++;
+                if (step >= a.n_steps) return;
+            }
+            const MegaPhase& ph = a.phases[pi];
+            if (ph.type != PH_ATTN) {
+                int r0;
+                mega_row_range(ph.N, ph.type == PH_GATEUP ? 2 : 1, blockIdx.x, G, r0, r1);
+                if (r0 < r1) {
+                    row = r0;
+                    RC = 8 / ph.ks;
+                    return;
+                }
+            }
+            pi++;
+        }
+    }
+    __device__ __forceinline__ void get(const MegaArgs& a, const uint16_t*& src, uint32_t& bytes) const {
+        const MegaPhase& ph = a.phases[pi];
+        src = ph.W + static_cast<size_t>(row) * ph.K;
+        bytes = static_cast<uint32_t>(min(RC, r1 - row)) * ph.K * 2;
+    }
+    __device__ __forceinline__ void next(const MegaArgs& a, int G) {
+        index++;
+        row += RC;
+        if (row >= r1) {
+            pi++;
+            seek_phase(a, G);
+        }
+    }
+};
+
+constexpr int kMegaL2Ahead = 16;  // chunks prefetched into L2 beyond the shared-memory ring
+
 __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const MegaArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     MegaSmem sm;
-    sm.ring = smem_raw;
-    uint8_t* p = smem_raw + static_cast<size_t>(a.n_stages) * kMegaStageBytes;
-    sm.full = reinterpret_cast<uint64_t*>(p);  p += 8 * kMegaMaxStages;
-    sm.empty = reinterpret_cast<uint64_t*>(p); p += 8 * kMegaMaxStages;
-    sm.keys = reinterpret_cast<unsigned long long*>(p); p += 8 * 8;
-    sm.red = reinterpret_cast<float*>(p);      p += 4 * 32;
-    sm.part = reinterpret_cast<float*>(p);     p += 4 * 16;
-    sm.xs = reinterpret_cast<float*>(p);       p += 4 * kMegaXsFloats;
-    sm.attn_scratch = reinterpret_cast<float*>(p);
+    sm.gen = reinterpret_cast<float*>(smem_raw);
+    sm.base = smem_u32(smem_raw);
+    sm.ring = sm.base;
+    uint32_t p = sm.base + static_cast<uint32_t>(a.n_stages) * kMegaStageBytes;
+    sm.full = p;  p += 8 * kMegaMaxStages;
+    sm.empty = p; p += 8 * kMegaMaxStages;
+    sm.keys = p;  p += 8 * 8;
+    sm.red = p;   p += 4 * 32;
+    sm.part = p;  p += 4 * 16;
+    sm.xs = p;    p += 4 * kMegaXsFloats;
+    sm.attn_scratch = p;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; s++) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], kMegaConsumerWarps);
+            mbar_init(reinterpret_cast<uint64_t*>(sm.generic(sm.full + s * 8)), 1);
+            mbar_init(reinterpret_cast<uint64_t*>(sm.generic(sm.empty + s * 8)), kMegaConsumerWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -512,40 +621,51 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const Mega
         // ================= producer warp: stream every weight chunk this CTA will ever need =================
         if (tid == kMegaConsumerThreads) {
             const uint64_t policy = l2_evict_first_policy();
-            uint32_t cc = 0;
-            for (int step = 0; step < a.n_steps; step++) {
-                for (int pi = 0; pi < a.n_phases; pi++) {
-                    const MegaPhase& ph = a.phases[pi];
-                    if (ph.type == PH_ATTN) continue;
-                    const int RC = 8 / ph.ks;
-                    int r0, r1;
-                    mega_row_range(ph.N, ph.type == PH_GATEUP ? 2 : 1, blockIdx.x, G, r0, r1);
-                    for (int row = r0; row < r1; row += RC, cc++) {
-                        const int stage = cc % a.n_stages;
-                        mbar_wait(&sm.empty[stage], ((cc / a.n_stages) & 1) ^ 1, a.abort_flag, 300 + ph.type);
-                        const uint32_t bytes = static_cast<uint32_t>(min(RC, r1 - row)) * ph.K * 2;
-                        mbar_arrive_expect_tx(&sm.full[stage], bytes);
-                        tma_bulk_g2s(sm.ring + static_cast<size_t>(stage) * kMegaStageBytes, ph.W + static_cast<size_t>(row) * ph.K,
-                                     bytes, &sm.full[stage], policy);
+            ChunkCursor ld{0, 0, 0, 0, 1, 0}, pf{0, 0, 0, 0, 1, 0};
+            ld.seek_phase(a, G);
+            pf.seek_phase(a, G);
+            RingPos rp{0, 0, a.n_stages};
+            while (!ld.done(a)) {
+                // HBM -> L2 runs kMegaL2Ahead chunks ahead of the ring, so HBM keeps streaming while
+                // the consumers sit in a grid barrier or in attention with the ring full
+                while (!pf.done(a) && pf.index < ld.index + a.n_stages + kMegaL2Ahead) {
+                    if (pf.index >= ld.index + a.n_stages) {
+                        const uint16_t* src;
+                        uint32_t bytes;
+                        pf.get(a, src, bytes);
+                        tma_prefetch_l2(src, bytes);
                     }
+                    pf.next(a, G);
                 }
+                mbar_wait(sm.empty + rp.stage * 8, rp.parity ^ 1, a.abort_flag, 300);
+                const uint16_t* src;
+                uint32_t bytes;
+                ld.get(a, src, bytes);
+                mbar_arrive_expect_tx(sm.full + rp.stage * 8, bytes);
+                tma_bulk_g2s(sm.ring + static_cast<uint32_t>(rp.stage) * kMegaStageBytes, src, bytes, sm.full + rp.stage * 8, policy);
+                rp.advance();
+                ld.next(a, G);
             }
         }
         return;
     }
 
     // ================= consumer warps =================
-    uint32_t cc = 0;
+    RingPos rp{0, 0, a.n_stages};
     unsigned long long nbar = 0;  // grid barriers passed in this launch
     int token = token0;
     for (int step = 0; step < a.n_steps; step++) {
         const int pos = pos0 + step;
         unsigned long long best_key = 0ull;
+        if (a.prof && step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == G - 1)) {
+            const unsigned long long t = globaltimer_ns();
+            a.prof[(blockIdx.x == 0 ? 0 : 2) * (a.n_phases + 1)] = t;
+            a.prof[(blockIdx.x == 0 ? 1 : 3) * (a.n_phases + 1)] = t;
+        }
         for (int pi = 0; pi < a.n_phases; pi++) {
             const MegaPhase& ph = a.phases[pi];
             if (ph.type == PH_ATTN) {
-                const int ctx = pos + 1;
-                const int nsplit = max(1, min(a.nsplit_max, (ctx + 63) / 64));
+                const int nsplit = mega_nsplit(a, pos + 1);
                 const int item = blockIdx.x;
                 if (item < a.nkv * nsplit) {
                     const int kvh = item / nsplit, split = item % nsplit;
@@ -555,14 +675,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const Mega
                 }
             } else {
                 switch (ph.m) {
-                    case 1: mega_gemv_phase<1>(a, ph, sm, cc, token, best_key, tid); break;
-                    case 2: mega_gemv_phase<2>(a, ph, sm, cc, token, best_key, tid); break;
-                    case 3: mega_gemv_phase<3>(a, ph, sm, cc, token, best_key, tid); break;
-                    case 4: mega_gemv_phase<4>(a, ph, sm, cc, token, best_key, tid); break;
-                    case 5: mega_gemv_phase<5>(a, ph, sm, cc, token, best_key, tid); break;
-                    case 6: mega_gemv_phase<6>(a, ph, sm, cc, token, best_key, tid); break;
-                    case 7: mega_gemv_phase<7>(a, ph, sm, cc, token, best_key, tid); break;
-                    default: mega_gemv_phase<8>(a, ph, sm, cc, token, best_key, tid); break;
+                    case 1: mega_gemv_phase<1>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                    case 2: mega_gemv_phase<2>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                    case 3: mega_gemv_phase<3>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                    case 4: mega_gemv_phase<4>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                    case 5: mega_gemv_phase<5>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                    case 6: mega_gemv_phase<6>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                    case 7: mega_gemv_phase<7>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                    default: mega_gemv_phase<8>(a, ph, sm, rp, token, pos, best_key, tid); break;
                 }
             }
             if (ph.type == PH_LMHEAD) {
@@ -573,17 +693,21 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const Mega
                     const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_key, o);
                     best_key = other > best_key ? other : best_key;
                 }
-                if (lane == 0) sm.keys[w] = best_key;
+                unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm.generic(sm.keys));
+                if (lane == 0) keys[w] = best_key;
                 consumer_bar();
                 if (tid == 0) {
-                    unsigned long long k = sm.keys[0];
-                    for (int i = 1; i < kMegaConsumerWarps; i++) k = sm.keys[i] > k ? sm.keys[i] : k;
+                    unsigned long long k = keys[0];
+                    for (int i = 1; i < kMegaConsumerWarps; i++) k = keys[i] > k ? keys[i] : k;
                     atomicMax(a.argmax_keys + (step % 3), k);
                 }
             }
             nbar++;
+            const bool prof = a.prof && step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == G - 1);
+            if (prof) a.prof[(blockIdx.x == 0 ? 0 : 2) * (a.n_phases + 1) + pi + 1] = globaltimer_ns();
             mega_grid_sync(a, epoch + nbar * G, tid);
-            if (pi == 1 && blockIdx.x == 0 && tid == 0) a.argmax_keys[(step + 1) % 3] = 0ull;  // safe: two barriers past its last reader
+            if (prof) a.prof[(blockIdx.x == 0 ? 1 : 3) * (a.n_phases + 1) + pi + 1] = globaltimer_ns();
+            if (pi == 1 && blockIdx.x == 0 && tid == 0) a.argmax_keys[(step + 1) % 3] = 0ull;  // last read two steps ago
         }
         token = argmax_key_index(ld_acquire_u64(a.argmax_keys + (step % 3)));
         if (blockIdx.x == 0 && tid == 0) a.out_ids[step] = token;
