@@ -310,7 +310,7 @@ void mega_setup(b2l_ctx* c) {
         MegaPhase p{};
         p.type = type; p.layer = layer; p.W = W; p.norm_w = norm; p.kv_pool = kv; p.N = N; p.K = K; p.ks = 1; p.m = 1;
         if (type != PH_ATTN && !mega_shape(K, &p.ks, &p.m)) return false;
-        if (type == PH_GATEUP && p.ks > 4) return false;
+        if (p.ks > kMegaRows) return false;  // a K slice of 4 rows must fit the 16 KB stages
         ph.push_back(p);
         return true;
     };
@@ -328,14 +328,22 @@ void mega_setup(b2l_ctx* c) {
     if (c->nkv_l > G) return no("more kv heads than SMs");
     c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
     const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
-    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 128 + 64 + sizeof(float) * kMegaXsFloats + attn_scratch + 256;
+    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 64 + 128 + 4 * 2 * kMegaConsumerWarps * kMegaRows + sizeof(float) * kMegaXsFloats + 48 * ph.size() + attn_scratch + 256;
     int max_smem = 0;
     B2L_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->p.device));
     const int stages = std::min<int>(kMegaMaxStages, static_cast<int>((static_cast<size_t>(max_smem) - fixed) / kMegaStageBytes));
-    if (stages < 2) return no("not enough shared memory for the weight ring");
+    if (stages < 8) return no("not enough shared memory for the weight ring");
     c->mega_stages = stages;
     c->mega_smem = static_cast<size_t>(stages) * kMegaStageBytes + fixed;
     B2L_CUDA(cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->mega_smem)));
+    {   // the kernel calls non-inlined device functions: make sure the per-thread stack covers its frames
+        cudaFuncAttributes fa{};
+        B2L_CUDA(cudaFuncGetAttributes(&fa, mega_decode_kernel));
+        size_t cur = 0;
+        B2L_CUDA(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
+        const size_t want = static_cast<size_t>(fa.localSizeBytes) + 2048;
+        if (cur < want) B2L_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, want));
+    }
     int per_sm = 0;
     B2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel, kMegaThreads, c->mega_smem));
     if (per_sm < 1) return no("megakernel does not fit on an SM");
@@ -345,8 +353,11 @@ void mega_setup(b2l_ctx* c) {
     c->mega_n_phases = static_cast<int>(ph.size());
     c->mega_bar = dalloc<unsigned long long>(c, 8);
     B2L_CUDA(cudaMemset(c->mega_bar, 0, sizeof(unsigned long long) * 8));
-    B2L_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->mega_abort), sizeof(int), cudaHostAllocMapped));
-    *c->mega_abort = 0;
+    B2L_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->mega_abort), sizeof(int) * 1024, cudaHostAllocMapped));
+    std::memset(c->mega_abort, 0, sizeof(int) * 1024);
+    if (const char* e = std::getenv("B2L_MEGA_INFLIGHT")) c->mega_inflight = std::atoi(e);   // tuning knobs
+    if (const char* e = std::getenv("B2L_MEGA_L2AHEAD")) c->mega_l2_ahead = std::atoi(e);
+    if (const char* e = std::getenv("B2L_MEGA_STAGES")) c->mega_stages = std::max(2, std::min(c->mega_stages, std::atoi(e)));
     c->mega_ok = true;
 }
 
@@ -369,6 +380,9 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     B2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_abort), c->mega_abort, 0));
     a.abort_flag = dev_abort;
     a.prof = c->mega_prof;
+    a.debug_progress = std::getenv("B2L_MEGA_DEBUG") ? 1 : 0;
+    a.max_inflight = c->mega_inflight;
+    a.l2_ahead = c->mega_l2_ahead;
     B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->prop.multiProcessorCount);
@@ -387,6 +401,11 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
 void mega_check(b2l_ctx* c, cudaError_t sync_result) {
     if (sync_result == cudaSuccess) return;
     const int code = c->mega_abort ? *c->mega_abort : 0;
+    if (c->mega_abort && std::getenv("B2L_MEGA_DEBUG")) {
+        std::fprintf(stderr, "megakernel progress markers (step*100000 + phase*100 + stage):");
+        for (int i = 0; i < c->prop.multiProcessorCount; i++) std::fprintf(stderr, " %d", c->mega_abort[1 + i]);
+        std::fprintf(stderr, "\n");
+    }
     throw Error(std::string("megakernel failed: ") + cudaGetErrorString(sync_result) + " (abort code " + std::to_string(code) +
                 "; 100 = grid barrier timeout, 2xx = consumer wait, 3xx = producer wait)");
 }
@@ -705,9 +724,13 @@ int b2l_decode_loop(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t*
             B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
             c->launched += static_cast<int64_t>(g.nodes) * n_steps;
         }
-        B2L_CUDA(cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
-        if (mega) mega_check(c, cudaStreamSynchronize(c->stream));
-        else B2L_CUDA(cudaStreamSynchronize(c->stream));
+        if (mega) {
+            mega_check(c, cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
+            mega_check(c, cudaStreamSynchronize(c->stream));
+        } else {
+            B2L_CUDA(cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
+            B2L_CUDA(cudaStreamSynchronize(c->stream));
+        }
         if (device_ms) B2L_CUDA(cudaEventElapsedTime(device_ms, c->ev0, c->ev1));
         c->logits_src = c->logits;
         c->logits_rows = n_seq;
@@ -833,7 +856,7 @@ int b2l_debug_mega_profile(b2l_ctx* c, int enable, uint64_t* out_ns, int* n_phas
     return guarded(c, [&] {
         require_ready(c);
         B2L_CHECK(c->mega_ok, "megakernel unavailable: " + c->mega_why);
-        const size_t n = 4 * static_cast<size_t>(c->mega_n_phases + 1);
+        const size_t n = 9 * static_cast<size_t>(c->mega_n_phases + 1);
         if (enable && !c->mega_prof) {
             c->mega_prof = dalloc<unsigned long long>(c, n);
             B2L_CUDA(cudaMemset(c->mega_prof, 0, n * 8));

@@ -23,8 +23,9 @@ namespace b2l {
 constexpr int kMegaConsumerWarps = 8;
 constexpr int kMegaConsumerThreads = kMegaConsumerWarps * 32;
 constexpr int kMegaThreads = kMegaConsumerThreads + 32;  // + producer warp
-constexpr int kMegaStageBytes = 32 * 1024;
-constexpr int kMegaMaxStages = 6;
+constexpr int kMegaStageBytes = 16 * 1024;
+constexpr int kMegaMaxStages = 12;
+constexpr int kMegaRows = 4;  // rows one warp reduces together (transposed butterfly)
 constexpr int kMegaXsFloats = 2048;
 
 enum MegaPhaseType { PH_QKV = 0, PH_ATTN = 1, PH_OPROJ = 2, PH_GATEUP = 3, PH_DOWN = 4, PH_LMHEAD = 5 };
@@ -35,8 +36,8 @@ struct MegaPhase {
     const uint16_t* norm_w;  // fused RMSNorm weight or null
     uint16_t* kv_pool;       // PH_ATTN: this layer's KV pool
     int N, K;
-    int ks;                  // warps per row (K split); rows per chunk = 8 / ks
-    int m;                   // 16-byte sweeps per warp unit: slice = 256 * m elements
+    int ks;                  // warps per row (K split into ks slices of 256*m elements)
+    int m;                   // 16-byte sweeps per warp unit: slice = 256 * m elements (<= 2048)
 };
 
 struct MegaArgs {
@@ -65,8 +66,11 @@ struct MegaArgs {
     unsigned long long* bar_counter;  // monotonically increasing arrivals
     unsigned long long* bar_epoch;    // arrivals consumed by previous launches
     unsigned long long* argmax_keys;  // [3]
-    int* abort_flag;
-    unsigned long long* prof;  // optional [4][n_phases + 1] globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
+    int* abort_flag;     // mapped pinned host memory: [0] abort code, [1 + cta] progress marker of each CTA (debug)
+    int debug_progress;  // 1: CTAs record step*100000 + phase*100 + stage-of-phase
+    int max_inflight;   // bulk copies issued but not yet landed, per CTA (bounds queueing latency in L2/HBM)
+    int l2_ahead;       // chunks prefetched into L2 beyond the ring (0 = off)
+    unsigned long long* prof;  // optional [9][n_phases + 1], see b2l_debug_mega_profile globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -78,8 +82,8 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // ---- PTX helpers ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -98,17 +102,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// a deadlock here would hang the GPU: bound every wait (~2 s) and trap with a reason code instead
-__device__ __noinline__ void mega_die(int* abort_flag, int code) {
-    atomicExch(abort_flag, code);
+// non-blocking probe (try_wait may suspend the thread for a hardware-defined time before failing)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// a deadlock here would hang the GPU: bound every wait and trap with a reason code instead.
+// Everything is inline (no calls in the hot loops: a call forces ABI spills around it).
+__device__ __forceinline__ void mega_die(int* abort_flag, int code) {
+    *reinterpret_cast<volatile int*>(abort_flag) = code;  // mapped pinned host memory
     __threadfence_system();
+    __nanosleep(2000000);  // give the store time to reach the host before the context dies
     __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag, int code) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    unsigned spins = 0;  // try_wait suspends for a hardware-defined interval per attempt
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) mega_die(abort_flag, code);
+        if (++spins > (1u << 24)) mega_die(abort_flag, code);
     }
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
@@ -138,6 +156,18 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
 __device__ __forceinline__ void sts128f(uint32_t addr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds64(uint32_t addr) {
+    unsigned long long r;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
 __device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -161,17 +191,15 @@ __device__ __forceinline__ void mega_grid_sync(const MegaArgs& a, unsigned long 
     if (tid == 0) {
         // release: cumulative over the CTA's writes ordered by the bar.sync above; readers use ld.global.cg
         red_release_add_u64(a.bar_counter, 1ull);
-        if (ld_acquire_u64(a.bar_counter) < target) {
-            const long long t0 = clock64();
-            while (ld_acquire_u64(a.bar_counter) < target) {
-                if (clock64() - t0 > 4000000000ll) mega_die(a.abort_flag, 100);
-            }
+        unsigned spins = 0;
+        while (ld_acquire_u64(a.bar_counter) < target) {
+            if (++spins > (1u << 24)) mega_die(a.abort_flag, 100);
         }
     }
     consumer_bar();
 }
 
-// ---- shared memory map (32-bit shared-space addresses, kept in registers) ---------------------
+// ---- shared memory map: 32-bit shared-space addresses, all kept in registers -----------------
 struct MegaSmem {
     uint32_t ring;          // [n_stages][kMegaStageBytes]
     uint32_t full, empty;   // [n_stages] mbarriers each
@@ -179,43 +207,81 @@ struct MegaSmem {
     uint32_t red;           // [32] fp32
     uint32_t part;          // [2][8] fp32 per-chunk partial sums (double buffered)
     uint32_t keys;          // [8] u64
+    uint32_t rel;           // [n_stages] u32: completed uses of each stage (see the consumer wait)
+    uint32_t phases;        // [n_phases] MegaPhase copies (static for the whole launch)
     uint32_t attn_scratch;
-    float* gen;             // generic pointer to the same block's base (for the few generic accesses)
-    uint32_t base;
-    __device__ __forceinline__ float* generic(uint32_t addr) const {
-        return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(gen) + (addr - base));
-    }
 };
+
+// a phase descriptor held in registers (read from the shared-memory copy)
+struct PhaseRegs {
+    int type, layer, N, K, ks, m;
+    const uint16_t* W;
+    const uint16_t* norm_w;
+    uint16_t* kv_pool;
+};
+static_assert(sizeof(MegaPhase) == 48, "MegaPhase is copied to shared memory as three 16-byte words");
+
+__device__ __forceinline__ PhaseRegs mega_load_phase(uint32_t phases, int pi) {
+    const uint4 a0 = lds128(phases + pi * 48), a1 = lds128(phases + pi * 48 + 16), a2 = lds128(phases + pi * 48 + 32);
+    PhaseRegs r;
+    r.type = static_cast<int>(a0.x);
+    r.layer = static_cast<int>(a0.y);
+    r.W = reinterpret_cast<const uint16_t*>(static_cast<unsigned long long>(a0.z) | (static_cast<unsigned long long>(a0.w) << 32));
+    r.norm_w = reinterpret_cast<const uint16_t*>(static_cast<unsigned long long>(a1.x) | (static_cast<unsigned long long>(a1.y) << 32));
+    r.kv_pool = reinterpret_cast<uint16_t*>(static_cast<unsigned long long>(a1.z) | (static_cast<unsigned long long>(a1.w) << 32));
+    r.N = static_cast<int>(a2.x);
+    r.K = static_cast<int>(a2.y);
+    r.ks = static_cast<int>(a2.z);
+    r.m = static_cast<int>(a2.w);
+    return r;
+}
 
 // position in the ring: stage index and phase parity, advanced incrementally (no div/mod per chunk)
 struct RingPos {
     int stage;
     uint32_t parity;
-    int n_stages;
-    __device__ __forceinline__ void advance() {
+    uint32_t use;  // how many times the ring has wrapped = earlier uses of `stage` (mod 2^32)
+    __device__ __forceinline__ void advance(int n_stages) {
         if (++stage == n_stages) {
             stage = 0;
             parity ^= 1;
+            use++;
         }
+    }
+    __device__ __forceinline__ RingPos plus(int k, int n_stages) const {
+        RingPos r{stage + k, parity, use};
+        while (r.stage >= n_stages) {
+            r.stage -= n_stages;
+            r.parity ^= 1;
+            r.use++;
+        }
+        return r;
     }
 };
 
-__device__ __forceinline__ int mega_nsplit(const MegaArgs& a, int ctx) { return max(1, min(a.nsplit_max, (ctx + 127) >> 7)); }
+// rows of a [N][K] matrix that one 16 KB ring stage holds
+__device__ __forceinline__ int mega_rows_per_stage(int ks) { return ks == 1 ? kMegaRows : kMegaRows / ks; }
 
-// attention output element k (head-major) of this step: merge the split-K partials
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
+
+__device__ __forceinline__ int mega_nsplit(int nsplit_max, int ctx) { return max(1, min(nsplit_max, (ctx + 127) >> 7)); }
+
+// attention output elements [k, k+8) of this step: merge the split-K partials
 __device__ __forceinline__ void mega_attn_combine8(const MegaArgs& a, int k, int nsplit, float* out) {
     const int head = k / a.hd, d = k % a.hd;  // 8 consecutive k never straddle a head (hd % 8 == 0)
     const int group = a.nh / a.nkv, kvh = head / group, g = head % group;
     const size_t rbase = static_cast<size_t>(kvh) * a.nsplit_max;
-    float M = -INFINITY;
-    for (int s = 0; s < nsplit; s++) M = fmaxf(M, __ldcg(a.part_ml + ((rbase + s) * group + g) * 2));
+    float Mx = -INFINITY;
+    for (int s = 0; s < nsplit; s++) Mx = fmaxf(Mx, __ldcg(a.part_ml + ((rbase + s) * group + g) * 2));
     float L = 0.f, acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
     for (int s = 0; s < nsplit; s++) {
         const float2 ml = __ldcg(reinterpret_cast<const float2*>(a.part_ml + ((rbase + s) * group + g) * 2));
         if (ml.x == -INFINITY) continue;
-        const float wgt = __expf(ml.x - M);
+        const float wgt = __expf(ml.x - Mx);
         L = fmaf(ml.y, wgt, L);
         const float* pa = a.part_acc + ((rbase + s) * group + g) * a.hd + d;
         const float4 p0 = __ldcg(reinterpret_cast<const float4*>(pa)), p1 = __ldcg(reinterpret_cast<const float4*>(pa + 4));
@@ -227,20 +293,72 @@ __device__ __forceinline__ void mega_attn_combine8(const MegaArgs& a, int k, int
     for (int i = 0; i < 8; i++) out[i] = acc[i] * inv;
 }
 
+// everything the consumer threads carry across phases, in registers
+struct ConsumerState {
+    RingPos rp;
+    unsigned long long nbar;      // grid barriers passed in this launch
+    unsigned long long epoch;
+    unsigned long long best_key;  // running argmax of this step's logits
+    int token, step;
+    bool need_barrier;            // false only for the very first phase of the launch
+};
+
+// barrier that precedes a phase: wait for the previous phase's outputs; at a token boundary also
+// pick up the argmax that becomes the next input token
+__device__ __forceinline__ void mega_phase_barrier(const MegaArgs& a, ConsumerState& st, bool token_boundary, int tid) {
+    if (!st.need_barrier) {
+        st.need_barrier = true;
+        return;
+    }
+    st.nbar++;
+    mega_grid_sync(a, st.epoch + st.nbar * gridDim.x, tid);
+    if (token_boundary) {
+        st.token = argmax_key_index(ld_acquire_u64(a.argmax_keys + ((st.step + 2) % 3)));  // previous step's key
+        if (blockIdx.x == 0 && tid == 0) a.out_ids[st.step - 1] = st.token;
+    }
+}
+
 // ---- one GEMV-type phase for one CTA ---------------------------------------------------------
-template <int M>
-__device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase& ph, const MegaSmem sm, RingPos& rp, int token,
-                                             int pos, unsigned long long& best_key, int tid) {
+#ifdef MEGA_GEMV_INLINE
+#define MEGA_GEMV_ATTR __forceinline__
+#else
+#define MEGA_GEMV_ATTR __noinline__
+#endif
+template <int M, bool SPLIT>  // SPLIT: K is split over ks > 1 warps
+__device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseRegs ph, const MegaSmem sm, ConsumerState& st_ref,
+                                             int pi, int pos, int tid) {
+    ConsumerState st = st_ref;  // work on a register copy; written back once at the end
     const int lane = tid & 31, w = tid >> 5;
-    const int ks = ph.ks, RC = 8 / ks, slice = 256 * M;
-    const int q = w % ks, rloc = w / ks;
+    const int ks = SPLIT ? ph.ks : 1, slice = 256 * M;
+    const int ks_shift = ks == 1 ? 0 : ks == 2 ? 1 : 2;  // ks in {1, 2, 4}
+    const int q = w & (ks - 1), rloc = w >> ks_shift;
     const int K = ph.K, type = ph.type;
+    const bool prof = a.prof && st.step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+    unsigned long long* prof_col = a.prof + pi;
+    const int prow = blockIdx.x == 0 ? 0 : 4, pstride = a.n_phases + 1;
+    if (prof) prof_col[(prow + 0) * pstride] = globaltimer_ns();
+    volatile int* progress = a.debug_progress && tid == 0 ? a.abort_flag + 1 + blockIdx.x : nullptr;
+    if (progress) *progress = st.step * 100000 + pi * 100 + 1;
+
+    // ---- static prologue: nothing here depends on other CTAs, so it overlaps the barrier wait ----
+    int r0, r1;
+    mega_row_range(ph.N, type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
+    uint4 nw[M];
+    if (ph.norm_w) {
+#pragma unroll
+        for (int i = 0; i < M; i++) nw[i] = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + q * slice + i * 256 + lane * 8));
+    }
+    const bool from_embed = (type == PH_QKV && ph.layer == 0);
+    mega_phase_barrier(a, st, from_embed && st.step > 0, tid);
+    if (prof) prof_col[(prow + 1) * pstride] = globaltimer_ns();
+    if (progress) *progress = st.step * 100000 + pi * 100 + 2;
+
     // ---- input vector -> registers (fused RMSNorm / split-K attention merge) ----
     const float* xsrc = type == PH_DOWN ? a.act : a.h;
-    const bool from_embed = (type == PH_QKV && ph.layer == 0);
-    const int nsplit = mega_nsplit(a, pos + 1);
+    const int nsplit = mega_nsplit(a.nsplit_max, pos + 1);
+    const int token = st.token;
     float xr[M * 8];
-    if (ks == 1) {
+    if (!SPLIT) {
         // every warp needs the same K floats: fetch once per CTA, then fan out through smem
         if (type == PH_OPROJ) {
             for (int k = tid * 8; k < K; k += kMegaConsumerThreads * 8) {
@@ -253,7 +371,7 @@ __device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase&
             for (int k = tid * 4; k < K; k += kMegaConsumerThreads * 4) {
                 float4 v;
                 if (from_embed) {
-                    const uint2 e = *reinterpret_cast<const uint2*>(a.embed + static_cast<size_t>(token) * a.H + k);
+                    const uint2 e = __ldg(reinterpret_cast<const uint2*>(a.embed + static_cast<size_t>(token) * a.H + k));
                     v = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
                 } else {
                     v = __ldcg(reinterpret_cast<const float4*>(xsrc + k));
@@ -278,7 +396,7 @@ __device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase&
             }
             float4 v0, v1;
             if (from_embed) {
-                const uint4 e = *reinterpret_cast<const uint4*>(a.embed + static_cast<size_t>(token) * a.H + k);
+                const uint4 e = __ldg(reinterpret_cast<const uint4*>(a.embed + static_cast<size_t>(token) * a.H + k));
                 v0 = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
                 v1 = make_float4(bf16lo(e.z), bf16hi(e.z), bf16lo(e.w), bf16hi(e.w));
             } else {
@@ -290,19 +408,17 @@ __device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase&
         }
     }
     if (ph.norm_w) {
-        uint4 nw[M];
-#pragma unroll
-        for (int i = 0; i < M; i++) nw[i] = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + q * slice + i * 256 + lane * 8));
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < M * 8; i++) ss = fmaf(xr[i], xr[i], ss);
         ss = warp_sum(ss);
-        float* red = sm.generic(sm.red);
-        if (lane == 0) red[w] = ss;
-        consumer_bar();
-        float tot = 0.f;
-        for (int i = 0; i < ks; i++) tot += red[i];  // warps 0..ks-1 hold slices 0..ks-1
-        const float inv = rsqrtf(tot / static_cast<float>(K) + a.eps);
+        if (SPLIT) {  // a warp holds only its K slice: add the other slices' sums (warps 0..ks-1)
+            if (lane == 0) sts32f(sm.red + w * 4, ss);
+            consumer_bar();
+            ss = 0.f;
+            for (int i = 0; i < ks; i++) ss += lds32f(sm.red + i * 4);
+        }
+        const float inv = rsqrtf(ss / static_cast<float>(K) + a.eps);
 #pragma unroll
         for (int i = 0; i < M; i++) {
             xr[i * 8 + 0] = bf16lo(nw[i].x) * (xr[i * 8 + 0] * inv);
@@ -315,91 +431,166 @@ __device__ __noinline__ void mega_gemv_phase(const MegaArgs& a, const MegaPhase&
             xr[i * 8 + 7] = bf16hi(nw[i].w) * (xr[i * 8 + 7] * inv);
         }
     }
+    if (prof) prof_col[(prow + 2) * pstride] = globaltimer_ns();
+    if (progress) *progress = st.step * 100000 + pi * 100 + 3;
 
-    // ---- stream this CTA's rows ----
-    int r0, r1;
-    mega_row_range(ph.N, type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
-    const int n_chunks = (r1 - r0 + RC - 1) / RC;
-    const bool cross = (ks > 1) || type == PH_GATEUP;  // result needs more than one warp
-    const uint32_t unit_off = (static_cast<uint32_t>(rloc) * K + static_cast<uint32_t>(q) * slice) * 2 + lane * 16;
-    float* part_base = sm.generic(sm.part);
-    for (int ch = 0; ch < n_chunks; ch++) {
-        const int row = r0 + ch * RC + rloc;
-        const bool valid = row < r1;
-        mbar_wait(sm.full + rp.stage * 8, rp.parity, a.abort_flag, 200 + type);
-        float acc[M];
-        if (valid) {
-            const uint32_t base = sm.ring + static_cast<uint32_t>(rp.stage) * kMegaStageBytes + unit_off;
-            uint4 wv[M];
+    // ---- stream this CTA's rows: a warp takes kMegaRows rows (x its K slice) at a time ----
+    const int RS = kMegaRows >> ks_shift, rs_shift = 2 - ks_shift;  // rows per ring stage (4, 2 or 1)
+    const int n_stage_total = (r1 - r0 + RS - 1) >> rs_shift;           // stages the producer fills for this phase
+    const bool resid_h = type == PH_DOWN || (type == PH_OPROJ && ph.layer != 0);
+    const bool resid_e = type == PH_OPROJ && ph.layer == 0;
+    const int my_t = lane >> 3;                         // after the butterfly, lane 8*t holds row t of the item
+    const bool out_lane = (lane & 7) == 0;
+    const bool hi16 = lane & 16, hi8 = lane & 8;
+    const int n_stages = a.n_stages;
+    int* const abort_flag = a.abort_flag;
+    unsigned long long best_key = st.best_key;
+    const RingPos rp0 = st.rp;
+    const int groups_per_round = kMegaConsumerWarps >> ks_shift;  // row groups (of kMegaRows rows) the CTA handles at once
+    const int n_groups = (r1 - r0 + kMegaRows - 1) / kMegaRows;
+    const int n_rounds = (n_groups + groups_per_round - 1) >> (3 - ks_shift);
+    const uint32_t lane_off = static_cast<uint32_t>(q) * slice * 2 + lane * 16;
+    // this warp's first item: row group rloc -> stage index rloc * ks
+    RingPos sp0 = rp0.plus(rloc * ks, n_stages);
+    const int stage_step = groups_per_round * ks;       // = kMegaConsumerWarps stages per round
+    for (int rd = 0; rd < n_rounds; rd++) {
+        const int rg = rd * groups_per_round + rloc;    // this warp's row group
+        const int row0 = r0 + rg * kMegaRows;
+        const bool live = rg < n_groups;
+        const int row_t = row0 + my_t;
+        const bool row_live = live && row_t < r1;
+        float resid = 0.f;  // residual input, fetched before the wait so its L2 latency overlaps
+        if (out_lane && row_live && q == 0) {
+            if (resid_h) resid = __ldcg(a.h + row_t);
+            else if (resid_e) resid = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row_t]);
+        }
+        float acc[kMegaRows][2];
 #pragma unroll
-            for (int i = 0; i < M; i++) wv[i] = lds128(base + i * 512);
+        for (int t = 0; t < kMegaRows; t++) acc[t][0] = acc[t][1] = 0.f;
+        if (live) {
+            uint32_t row_addr[kMegaRows];  // shared address of (row t, this warp's K slice, this lane)
+            const int first_stage = rg * ks;
+            {
+                RingPos sp = sp0;
+#pragma unroll
+                for (int j = 0; j < kMegaRows; j++) {  // stage j of this item holds rows [j*RS, (j+1)*RS)
+                    if (j < ks) {
+                        const bool exists = first_stage + j < n_stage_total;
+                        if (exists) {
+                            // Successive uses of a stage belong to different warps, so this warp can get
+                            // here before the PREVIOUS use has even landed, and a parity wait cannot tell
+                            // "one phase behind" from "done". The release counter of the previous use is
+                            // the proof that it landed (its reader finished); only then is the parity wait
+                            // unambiguous. (Usually satisfied on the first load.)
+                            unsigned spins = 0;
+                            for (;;) {
+                                uint32_t done;
+                                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(sm.rel + sp.stage * 4) : "memory");
+                                if (static_cast<int32_t>(done - sp.use) >= 0) break;
+                                if (++spins > (1u << 28)) mega_die(abort_flag, 210 + type);
+                            }
+                            mbar_wait(sm.full + sp.stage * 8, sp.parity, abort_flag, 200 + type);
+                        }
+                        const uint32_t base = sm.ring + static_cast<uint32_t>(sp.stage) * kMegaStageBytes + lane_off;
+#pragma unroll
+                        for (int t = 0; t < kMegaRows; t++) {
+                            if ((t >> rs_shift) == j) row_addr[t] = exists && (row0 + t < r1) ? base + static_cast<uint32_t>(t & (RS - 1)) * K * 2 : sm.xs;
+                        }
+                        sp.advance(n_stages);
+                    }
+                }
+            }
+            uint4 wv[2][kMegaRows];
+#pragma unroll
+            for (int t = 0; t < kMegaRows; t++) wv[0][t] = lds128(row_addr[t]);
 #pragma unroll
             for (int i = 0; i < M; i++) {
-                float s = bf16lo(wv[i].x) * xr[i * 8 + 0];
-                s = fmaf(bf16hi(wv[i].x), xr[i * 8 + 1], s);
-                s = fmaf(bf16lo(wv[i].y), xr[i * 8 + 2], s);
-                s = fmaf(bf16hi(wv[i].y), xr[i * 8 + 3], s);
-                s = fmaf(bf16lo(wv[i].z), xr[i * 8 + 4], s);
-                s = fmaf(bf16hi(wv[i].z), xr[i * 8 + 5], s);
-                s = fmaf(bf16lo(wv[i].w), xr[i * 8 + 6], s);
-                s = fmaf(bf16hi(wv[i].w), xr[i * 8 + 7], s);
-                acc[i] = s;
+                if (i + 1 < M) {
+#pragma unroll
+                    for (int t = 0; t < kMegaRows; t++) wv[(i + 1) & 1][t] = lds128(row_addr[t] + (i + 1) * 512);
+                }
+#pragma unroll
+                for (int t = 0; t < kMegaRows; t++) {
+                    const uint4 v = wv[i & 1][t];
+                    float sacc = acc[t][i & 1];
+                    sacc = fmaf(bf16lo(v.x), xr[i * 8 + 0], sacc);
+                    sacc = fmaf(bf16hi(v.x), xr[i * 8 + 1], sacc);
+                    sacc = fmaf(bf16lo(v.y), xr[i * 8 + 2], sacc);
+                    sacc = fmaf(bf16hi(v.y), xr[i * 8 + 3], sacc);
+                    sacc = fmaf(bf16lo(v.z), xr[i * 8 + 4], sacc);
+                    sacc = fmaf(bf16hi(v.z), xr[i * 8 + 5], sacc);
+                    sacc = fmaf(bf16lo(v.w), xr[i * 8 + 6], sacc);
+                    sacc = fmaf(bf16hi(v.w), xr[i * 8 + 7], sacc);
+                    acc[t][i & 1] = sacc;
+                }
             }
-        } else {
+            __syncwarp();
+            if (lane == 0) {  // hand the stage(s) back: kMegaRows arrivals per stage in total
+                {
+                    RingPos rel = sp0;
 #pragma unroll
-            for (int i = 0; i < M; i++) acc[i] = 0.f;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sm.empty + rp.stage * 8);  // smem slot can be refilled
-        rp.advance();
-        // tree-add the M sweep sums, then across lanes
-#pragma unroll
-        for (int st = 1; st < M; st <<= 1) {
-#pragma unroll
-            for (int i = 0; i + st < M; i += 2 * st) acc[i] += acc[i + st];
-        }
-        float s = warp_sum(acc[0]);
-        if (cross) {
-            float* part = part_base + (ch & 1) * 8;
-            if (lane == 0) part[w] = s;
-            consumer_bar();
-            if (q != 0 || (type == PH_GATEUP && (rloc & 1))) continue;  // one finalising warp per row / pair
-            s = 0.f;
-            for (int i = 0; i < ks; i++) s += part[w + i];
-            if (type == PH_GATEUP) {
-                float u = 0.f;
-                for (int i = 0; i < ks; i++) u += part[w + ks + i];
-                s = (s / (1.0f + __expf(-s))) * u;  // silu(gate) * up
-            }
-        }
-        if (lane == 0 && valid) {
-            switch (type) {
-                case PH_QKV: a.qkv[row] = s; break;
-                case PH_GATEUP: a.act[row >> 1] = s; break;
-                case PH_OPROJ:
-                    if (ph.layer == 0)
-                        a.h[row] = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row]) + s;
-                    else
-                        a.h[row] = __ldcg(a.h + row) + s;
-                    break;
-                case PH_DOWN: a.h[row] = __ldcg(a.h + row) + s; break;
-                default: {  // PH_LMHEAD
-                    a.logits[row] = s;
-                    const unsigned long long key = argmax_key(s, row);
-                    best_key = key > best_key ? key : best_key;
+                    for (int j = 0; j < kMegaRows; j++) {
+                        if (j < ks && first_stage + j < n_stage_total) {
+                            mbar_arrive_n(sm.empty + rel.stage * 8, kMegaRows >> ks_shift);
+                            asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sm.rel + rel.stage * 4), "r"(rel.use + 1) : "memory");
+                        }
+                        rel.advance(n_stages);
+                    }
                 }
             }
         }
+        sp0 = sp0.plus(stage_step, n_stages);
+        // transposed butterfly: 6 shuffles reduce all four rows; lane 8*t ends up with row t's sum.
+        // Rows past the end of the range read a duplicate row; their sums are never stored.
+        const float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1], a2 = acc[2][0] + acc[2][1], a3 = acc[3][0] + acc[3][1];
+        float s0 = hi16 ? a2 : a0, s1 = hi16 ? a3 : a1;
+        s0 += __shfl_xor_sync(0xffffffffu, hi16 ? a0 : a2, 16);
+        s1 += __shfl_xor_sync(0xffffffffu, hi16 ? a1 : a3, 16);
+        float s = (hi8 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, hi8 ? s0 : s1, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (SPLIT) {
+            // K was split over ks warps: add the slices through smem (one CTA barrier per round)
+            const uint32_t part = sm.part + (rd & 1) * (kMegaConsumerWarps * kMegaRows * 4);
+            if (out_lane) sts32f(part + (w * kMegaRows + my_t) * 4, row_live ? s : 0.f);
+            consumer_bar();
+            if (q != 0) continue;
+            s = 0.f;
+            for (int i = 0; i < ks; i++) s += lds32f(part + ((w + i) * kMegaRows + my_t) * 4);
+        }
+        if (type == PH_GATEUP) {
+            const float up = __shfl_down_sync(0xffffffffu, s, 8);  // rows are (gate, up) pairs
+            s = (s / (1.0f + __expf(-s))) * up;
+        }
+        if (out_lane && row_live) {
+            if (type == PH_QKV) {
+                a.qkv[row_t] = s;
+            } else if (type == PH_GATEUP) {
+                if ((my_t & 1) == 0) a.act[row_t >> 1] = s;
+            } else if (type == PH_LMHEAD) {
+                a.logits[row_t] = s;
+                const unsigned long long key = argmax_key(s, row_t);
+                best_key = key > best_key ? key : best_key;
+            } else {
+                a.h[row_t] = resid + s;  // O-proj / down: residual add
+            }
+        }
     }
+    st.rp = rp0.plus(n_stage_total, n_stages);
+    st.best_key = best_key;
+    st_ref = st;
+    if (progress) *progress = st.step * 100000 + pi * 100 + 4;
+    if (prof) prof_col[(prow + 3) * pstride] = globaltimer_ns();
 }
 
 // ---- attention work item: (kv head, split); partials are merged by the O-proj phase's x load -----
 template <int HD, int GROUP>
-__device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& ph, const MegaSmem sm, int kvh, int split,
-                                            int nsplit, int pos, int tid) {
+__device__ __noinline__ void mega_attn_item(const MegaArgs& a, uint16_t* kv_pool, uint32_t scratch, int kvh, int split, int nsplit,
+                                            int pos, int tid) {
     constexpr int LPT = HD / 8, TPW = 32 / LPT, HALF = HD / 2;
     const int lane = tid & 31, w = tid >> 5, sub = lane / LPT, sl = lane % LPT;
-    const KvLayout kv{ph.kv_pool, a.page_size, a.kvd};
+    const KvLayout kv{kv_pool, a.page_size, a.kvd};
     const int ctx = pos + 1;
     const int chunk = (ctx + nsplit - 1) / nsplit;
     const int j0 = split * chunk, j1 = min(ctx, j0 + chunk);
@@ -494,17 +685,17 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
             m[g] = mn;
         }
     }
-    // per-warp results -> smem: [w][g][HD] then (m, l)
-    float* s_acc = sm.generic(sm.attn_scratch);               // [8][GROUP][HD]
-    float* s_ml = s_acc + kMegaConsumerWarps * GROUP * HD;    // [8][GROUP][2]
+    // per-warp results -> smem: acc [w][g][HD], then (m, l) [w][g][2]
+    const uint32_t s_acc = scratch, s_ml = scratch + kMegaConsumerWarps * GROUP * HD * 4;
     if (sub == 0) {
 #pragma unroll
         for (int g = 0; g < GROUP; g++) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) s_acc[(w * GROUP + g) * HD + sl * 8 + i] = acc[g][i];
+            const uint32_t dst = s_acc + ((w * GROUP + g) * HD + sl * 8) * 4;
+            sts128f(dst, make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]));
+            sts128f(dst + 16, make_float4(acc[g][4], acc[g][5], acc[g][6], acc[g][7]));
             if (sl == 0) {
-                s_ml[(w * GROUP + g) * 2] = m[g];
-                s_ml[(w * GROUP + g) * 2 + 1] = l[g];
+                sts32f(s_ml + (w * GROUP + g) * 8, m[g]);
+                sts32f(s_ml + (w * GROUP + g) * 8 + 4, l[g]);
             }
         }
     }
@@ -514,14 +705,14 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
         const int g = e / HD, d = e % HD;
         float Mx = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < kMegaConsumerWarps; t++) Mx = fmaxf(Mx, s_ml[(t * GROUP + g) * 2]);
+        for (int t = 0; t < kMegaConsumerWarps; t++) Mx = fmaxf(Mx, lds32f(s_ml + (t * GROUP + g) * 8));
         float L = 0.f, A = 0.f;
         if (Mx > -INFINITY) {
 #pragma unroll
             for (int t = 0; t < kMegaConsumerWarps; t++) {
-                const float wgt = __expf(s_ml[(t * GROUP + g) * 2] - Mx);
-                L = fmaf(s_ml[(t * GROUP + g) * 2 + 1], wgt, L);
-                A = fmaf(s_acc[(t * GROUP + g) * HD + d], wgt, A);
+                const float wgt = __expf(lds32f(s_ml + (t * GROUP + g) * 8) - Mx);
+                L = fmaf(lds32f(s_ml + (t * GROUP + g) * 8 + 4), wgt, L);
+                A = fmaf(lds32f(s_acc + ((t * GROUP + g) * HD + d) * 4), wgt, A);
             }
         }
         a.part_acc[(pbase * GROUP + g) * HD + d] = A;
@@ -533,189 +724,230 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, const MegaPhase& 
 }
 
 template <int HD>
-__device__ __forceinline__ void mega_attn_group(const MegaArgs& a, const MegaPhase& ph, const MegaSmem& sm, int kvh, int split,
+__device__ __forceinline__ void mega_attn_group(const MegaArgs& a, uint16_t* kv_pool, uint32_t scratch, int kvh, int split,
                                                 int nsplit, int pos, int tid) {
     switch (a.nh / a.nkv) {
-        case 1: mega_attn_item<HD, 1>(a, ph, sm, kvh, split, nsplit, pos, tid); break;
-        case 2: mega_attn_item<HD, 2>(a, ph, sm, kvh, split, nsplit, pos, tid); break;
-        case 3: mega_attn_item<HD, 3>(a, ph, sm, kvh, split, nsplit, pos, tid); break;
-        case 4: mega_attn_item<HD, 4>(a, ph, sm, kvh, split, nsplit, pos, tid); break;
-        default: mega_attn_item<HD, 8>(a, ph, sm, kvh, split, nsplit, pos, tid); break;
+        case 1: mega_attn_item<HD, 1>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
+        case 2: mega_attn_item<HD, 2>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
+        case 3: mega_attn_item<HD, 3>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
+        case 4: mega_attn_item<HD, 4>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
+        default: mega_attn_item<HD, 8>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
     }
 }
 
-// the producer's view of the weight stream: every chunk this CTA needs, in model order, forever
+// the producer's view of the weight stream: every chunk this CTA needs, in model order, step after step
 struct ChunkCursor {
-    int step, pi, row, r1, RC;
+    int step, pi, row, r1, RC, K;
+    const uint16_t* W;
     long long index;
-    __device__ __forceinline__ bool done(const MegaArgs& a) const { return step >= a.n_steps; }
-    __device__ __forceinline__ void seek_phase(const MegaArgs& a, int G) {
+    __device__ __forceinline__ bool done(int n_steps) const { return step >= n_steps; }
+    __device__ __forceinline__ void seek_phase(uint32_t phases, int n_phases, int n_steps) {
         // move to the first row of the next phase that has weights and rows for this CTA
         for (;;) {
-            if (pi >= a.n_phases) {
+            if (pi >= n_phases) {
                 pi = 0;
                 step++;
-                if (step >= a.n_steps) return;
+                if (step >= n_steps) return;
             }
-            const MegaPhase& ph = a.phases[pi];
+            const PhaseRegs ph = mega_load_phase(phases, pi);
             if (ph.type != PH_ATTN) {
                 int r0;
-                mega_row_range(ph.N, ph.type == PH_GATEUP ? 2 : 1, blockIdx.x, G, r0, r1);
+                mega_row_range(ph.N, ph.type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
                 if (r0 < r1) {
                     row = r0;
-                    RC = 8 / ph.ks;
+                    RC = mega_rows_per_stage(ph.ks);
+                    K = ph.K;
+                    W = ph.W;
                     return;
                 }
             }
             pi++;
         }
     }
-    __device__ __forceinline__ void get(const MegaArgs& a, const uint16_t*& src, uint32_t& bytes) const {
-        const MegaPhase& ph = a.phases[pi];
-        src = ph.W + static_cast<size_t>(row) * ph.K;
-        bytes = static_cast<uint32_t>(min(RC, r1 - row)) * ph.K * 2;
+    __device__ __forceinline__ void get(const uint16_t*& src, uint32_t& bytes) const {
+        src = W + static_cast<size_t>(row) * K;
+        bytes = static_cast<uint32_t>(min(RC, r1 - row)) * K * 2;
     }
-    __device__ __forceinline__ void next(const MegaArgs& a, int G) {
+    __device__ __forceinline__ void next(uint32_t phases, int n_phases, int n_steps) {
         index++;
         row += RC;
         if (row >= r1) {
             pi++;
-            seek_phase(a, G);
+            seek_phase(phases, n_phases, n_steps);
         }
     }
 };
 
-constexpr int kMegaL2Ahead = 16;  // chunks prefetched into L2 beyond the shared-memory ring
-
-__global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const MegaArgs a) {
+__global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const __grid_constant__ MegaArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     MegaSmem sm;
-    sm.gen = reinterpret_cast<float*>(smem_raw);
-    sm.base = smem_u32(smem_raw);
-    sm.ring = sm.base;
-    uint32_t p = sm.base + static_cast<uint32_t>(a.n_stages) * kMegaStageBytes;
+    sm.ring = smem_u32(smem_raw);
+    uint32_t p = sm.ring + static_cast<uint32_t>(a.n_stages) * kMegaStageBytes;
     sm.full = p;  p += 8 * kMegaMaxStages;
     sm.empty = p; p += 8 * kMegaMaxStages;
     sm.keys = p;  p += 8 * 8;
+    sm.rel = p;   p += 4 * 16;
     sm.red = p;   p += 4 * 32;
-    sm.part = p;  p += 4 * 16;
+    sm.part = p;  p += 4 * 2 * kMegaConsumerWarps * kMegaRows;
     sm.xs = p;    p += 4 * kMegaXsFloats;
+    sm.phases = p; p += 48 * static_cast<uint32_t>(a.n_phases);
     sm.attn_scratch = p;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; s++) {
-            mbar_init(reinterpret_cast<uint64_t*>(sm.generic(sm.full + s * 8)), 1);
-            mbar_init(reinterpret_cast<uint64_t*>(sm.generic(sm.empty + s * 8)), kMegaConsumerWarps);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sm.rel + s * 4), "r"(0u) : "memory");
+            mbar_init(sm.full + s * 8, 1);
+            mbar_init(sm.empty + s * 8, kMegaRows);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    {   // phase table -> shared memory (static for the whole launch)
+        const uint4* src = reinterpret_cast<const uint4*>(a.phases);
+        for (int i = tid; i < a.n_phases * 3; i += kMegaThreads) {
+            const uint4 v = __ldg(src + i);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sm.phases + i * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+    }
     __syncthreads();
 
-    const int G = gridDim.x;
-    const unsigned long long epoch = *a.bar_epoch;
     const int pos0 = *a.position;
-    const int token0 = *a.token;
 
     if (tid >= kMegaConsumerThreads) {
         // ================= producer warp: stream every weight chunk this CTA will ever need =================
         if (tid == kMegaConsumerThreads) {
             const uint64_t policy = l2_evict_first_policy();
-            ChunkCursor ld{0, 0, 0, 0, 1, 0}, pf{0, 0, 0, 0, 1, 0};
-            ld.seek_phase(a, G);
-            pf.seek_phase(a, G);
-            RingPos rp{0, 0, a.n_stages};
-            while (!ld.done(a)) {
-                // HBM -> L2 runs kMegaL2Ahead chunks ahead of the ring, so HBM keeps streaming while
-                // the consumers sit in a grid barrier or in attention with the ring full
-                while (!pf.done(a) && pf.index < ld.index + a.n_stages + kMegaL2Ahead) {
+            ChunkCursor ld{0, 0, 0, 0, 1, 0, nullptr, 0}, pf{0, 0, 0, 0, 1, 0, nullptr, 0};
+            ld.seek_phase(sm.phases, a.n_phases, a.n_steps);
+            pf.seek_phase(sm.phases, a.n_phases, a.n_steps);
+            RingPos rp{0, 0, 0};
+            RingPos landed{0, 0, 0};  // oldest copy not yet known to have landed
+            int outstanding = 0;
+            while (!ld.done(a.n_steps)) {
+                // optional: HBM -> L2 runs l2_ahead chunks ahead of the ring
+                while (a.l2_ahead > 0 && !pf.done(a.n_steps) && pf.index < ld.index + a.n_stages + a.l2_ahead) {
                     if (pf.index >= ld.index + a.n_stages) {
                         const uint16_t* src;
                         uint32_t bytes;
-                        pf.get(a, src, bytes);
+                        pf.get(src, bytes);
                         tma_prefetch_l2(src, bytes);
                     }
-                    pf.next(a, G);
+                    pf.next(sm.phases, a.n_phases, a.n_steps);
+                }
+                // optional cap on copies issued but not yet landed
+                if (a.max_inflight > 0) {
+                    while (outstanding > 0 && mbar_test_wait(sm.full + landed.stage * 8, landed.parity)) {
+                        landed.advance(a.n_stages);
+                        outstanding--;
+                    }
+                    if (outstanding >= a.max_inflight) {
+                        mbar_wait(sm.full + landed.stage * 8, landed.parity, a.abort_flag, 310);
+                        landed.advance(a.n_stages);
+                        outstanding--;
+                    }
                 }
                 mbar_wait(sm.empty + rp.stage * 8, rp.parity ^ 1, a.abort_flag, 300);
                 const uint16_t* src;
                 uint32_t bytes;
-                ld.get(a, src, bytes);
+                ld.get(src, bytes);
                 mbar_arrive_expect_tx(sm.full + rp.stage * 8, bytes);
                 tma_bulk_g2s(sm.ring + static_cast<uint32_t>(rp.stage) * kMegaStageBytes, src, bytes, sm.full + rp.stage * 8, policy);
-                rp.advance();
-                ld.next(a, G);
+                rp.advance(a.n_stages);
+                outstanding++;
+                ld.next(sm.phases, a.n_phases, a.n_steps);
             }
         }
         return;
     }
 
     // ================= consumer warps =================
-    RingPos rp{0, 0, a.n_stages};
-    unsigned long long nbar = 0;  // grid barriers passed in this launch
-    int token = token0;
+    ConsumerState st;
+    st.rp = RingPos{0, 0, 0};
+    st.nbar = 0;
+    st.epoch = *a.bar_epoch;
+    st.best_key = 0ull;
+    st.token = *a.token;
+    st.step = 0;
+    st.need_barrier = false;
     for (int step = 0; step < a.n_steps; step++) {
         const int pos = pos0 + step;
-        unsigned long long best_key = 0ull;
-        if (a.prof && step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == G - 1)) {
-            const unsigned long long t = globaltimer_ns();
-            a.prof[(blockIdx.x == 0 ? 0 : 2) * (a.n_phases + 1)] = t;
-            a.prof[(blockIdx.x == 0 ? 1 : 3) * (a.n_phases + 1)] = t;
-        }
+        st.step = step;
+        st.best_key = 0ull;
         for (int pi = 0; pi < a.n_phases; pi++) {
-            const MegaPhase& ph = a.phases[pi];
+            const PhaseRegs ph = mega_load_phase(sm.phases, pi);
             if (ph.type == PH_ATTN) {
-                const int nsplit = mega_nsplit(a, pos + 1);
+                const bool prof = a.prof && step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+                const int prow = blockIdx.x == 0 ? 0 : 4, pstride = a.n_phases + 1;
+                if (prof) a.prof[(prow + 0) * pstride + pi] = globaltimer_ns();
+                mega_phase_barrier(a, st, false, tid);
+                if (prof) a.prof[(prow + 1) * pstride + pi] = a.prof[(prow + 2) * pstride + pi] = globaltimer_ns();
+                const int nsplit = mega_nsplit(a.nsplit_max, pos + 1);
                 const int item = blockIdx.x;
                 if (item < a.nkv * nsplit) {
                     const int kvh = item / nsplit, split = item % nsplit;
-                    if (a.hd == 64) mega_attn_group<64>(a, ph, sm, kvh, split, nsplit, pos, tid);
-                    else if (a.hd == 128) mega_attn_group<128>(a, ph, sm, kvh, split, nsplit, pos, tid);
-                    else mega_attn_group<32>(a, ph, sm, kvh, split, nsplit, pos, tid);
+                    if (a.hd == 64) mega_attn_group<64>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
+                    else if (a.hd == 128) mega_attn_group<128>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
+                    else mega_attn_group<32>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
                 }
+                if (prof) a.prof[(prow + 3) * pstride + pi] = globaltimer_ns();
             } else {
-                switch (ph.m) {
-                    case 1: mega_gemv_phase<1>(a, ph, sm, rp, token, pos, best_key, tid); break;
-                    case 2: mega_gemv_phase<2>(a, ph, sm, rp, token, pos, best_key, tid); break;
-                    case 3: mega_gemv_phase<3>(a, ph, sm, rp, token, pos, best_key, tid); break;
-                    case 4: mega_gemv_phase<4>(a, ph, sm, rp, token, pos, best_key, tid); break;
-                    case 5: mega_gemv_phase<5>(a, ph, sm, rp, token, pos, best_key, tid); break;
-                    case 6: mega_gemv_phase<6>(a, ph, sm, rp, token, pos, best_key, tid); break;
-                    case 7: mega_gemv_phase<7>(a, ph, sm, rp, token, pos, best_key, tid); break;
-                    default: mega_gemv_phase<8>(a, ph, sm, rp, token, pos, best_key, tid); break;
+                if (ph.ks == 1) {
+                    switch (ph.m) {
+                        case 1: mega_gemv_phase<1, false>(a, ph, sm, st, pi, pos, tid); break;
+                        case 2: mega_gemv_phase<2, false>(a, ph, sm, st, pi, pos, tid); break;
+                        case 3: mega_gemv_phase<3, false>(a, ph, sm, st, pi, pos, tid); break;
+                        case 4: mega_gemv_phase<4, false>(a, ph, sm, st, pi, pos, tid); break;
+                        case 5: mega_gemv_phase<5, false>(a, ph, sm, st, pi, pos, tid); break;
+                        case 6: mega_gemv_phase<6, false>(a, ph, sm, st, pi, pos, tid); break;
+                        case 7: mega_gemv_phase<7, false>(a, ph, sm, st, pi, pos, tid); break;
+                        default: mega_gemv_phase<8, false>(a, ph, sm, st, pi, pos, tid); break;
+                    }
+                } else {
+                    switch (ph.m) {
+                        case 1: mega_gemv_phase<1, true>(a, ph, sm, st, pi, pos, tid); break;
+                        case 2: mega_gemv_phase<2, true>(a, ph, sm, st, pi, pos, tid); break;
+                        case 3: mega_gemv_phase<3, true>(a, ph, sm, st, pi, pos, tid); break;
+                        case 4: mega_gemv_phase<4, true>(a, ph, sm, st, pi, pos, tid); break;
+                        case 5: mega_gemv_phase<5, true>(a, ph, sm, st, pi, pos, tid); break;
+                        case 6: mega_gemv_phase<6, true>(a, ph, sm, st, pi, pos, tid); break;
+                        case 7: mega_gemv_phase<7, true>(a, ph, sm, st, pi, pos, tid); break;
+                        default: mega_gemv_phase<8, true>(a, ph, sm, st, pi, pos, tid); break;
+                    }
                 }
             }
             if (ph.type == PH_LMHEAD) {
                 // CTA-level argmax, then one atomicMax per CTA on this step's key
                 const int lane = tid & 31, w = tid >> 5;
+                unsigned long long best_key = st.best_key;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_key, o);
                     best_key = other > best_key ? other : best_key;
                 }
-                unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm.generic(sm.keys));
-                if (lane == 0) keys[w] = best_key;
+                if (lane == 0) sts64(sm.keys + w * 8, best_key);
                 consumer_bar();
                 if (tid == 0) {
-                    unsigned long long k = keys[0];
-                    for (int i = 1; i < kMegaConsumerWarps; i++) k = keys[i] > k ? keys[i] : k;
+                    unsigned long long k = lds64(sm.keys);
+                    for (int i = 1; i < kMegaConsumerWarps; i++) {
+                        const unsigned long long o = lds64(sm.keys + i * 8);
+                        k = o > k ? o : k;
+                    }
                     atomicMax(a.argmax_keys + (step % 3), k);
                 }
             }
-            nbar++;
-            const bool prof = a.prof && step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == G - 1);
-            if (prof) a.prof[(blockIdx.x == 0 ? 0 : 2) * (a.n_phases + 1) + pi + 1] = globaltimer_ns();
-            mega_grid_sync(a, epoch + nbar * G, tid);
-            if (prof) a.prof[(blockIdx.x == 0 ? 1 : 3) * (a.n_phases + 1) + pi + 1] = globaltimer_ns();
-            if (pi == 1 && blockIdx.x == 0 && tid == 0) a.argmax_keys[(step + 1) % 3] = 0ull;  // last read two steps ago
+            // the key two steps ahead was last read at the start of the previous step: safe to clear now
+            if (pi == 2 && blockIdx.x == 0 && tid == 0) a.argmax_keys[(step + 1) % 3] = 0ull;
         }
-        token = argmax_key_index(ld_acquire_u64(a.argmax_keys + (step % 3)));
-        if (blockIdx.x == 0 && tid == 0) a.out_ids[step] = token;
     }
+    // final barrier: every CTA's lm_head rows are in the last key
+    st.nbar++;
+    mega_grid_sync(a, st.epoch + st.nbar * gridDim.x, tid);
+    const int token = argmax_key_index(ld_acquire_u64(a.argmax_keys + ((a.n_steps - 1) % 3)));
     if (blockIdx.x == 0 && tid == 0) {
+        a.out_ids[a.n_steps - 1] = token;
         *a.token = token;
         *a.position = pos0 + a.n_steps;
-        *a.bar_epoch = epoch + nbar * G;
+        *a.bar_epoch = st.epoch + st.nbar * gridDim.x;
     }
 }
 

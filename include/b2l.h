@@ -124,8 +124,9 @@ int b2l_get_info(b2l_ctx* c, b2l_info* out);
 int b2l_set_decode_mode(b2l_ctx* c, int mode);
 
 /* Debug: per-phase device timestamps (globaltimer ns) of the last token of the last megakernel
- * launch. enable=1 arms it; out_ns (optional) is [4][n_phases+1]: CTA 0 phase-end, CTA 0
- * barrier-exit, last CTA phase-end, last CTA barrier-exit (index 0 = token start).
+ * launch. enable=1 arms it; out_ns (optional) is [9][n_phases+1], column = phase: rows 0-3 CTA 0
+ * {phase entry, dependency barrier passed, input vector loaded, phase end}, rows 4-7 the same for
+ * the last CTA, row 8 CTA 0 warp 0 cycles spent waiting for weights.
  * phase_types (optional) [n_phases]: 0 qkv 1 attn 2 o 3 gate/up 4 down 5 lm_head. */
 int b2l_debug_mega_profile(b2l_ctx* c, int enable, uint64_t* out_ns, int* n_phases, int32_t* phase_types);
 

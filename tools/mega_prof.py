@@ -1,8 +1,10 @@
-"""Debug: per-phase timeline of the decode megakernel (1B, ctx 512)."""
-import sys, numpy as np
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+"""Debug: per-phase timeline of the decode megakernel (Llama-3.2-1B shapes, context 512)."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from gabby_b200 import synth
+
 arch = synth.preset("1b")
 eng = bench.build_engine(arch, 0, 1024)
 bt = np.arange(eng.max_blocks, dtype=np.int32)[None, :]
@@ -10,17 +12,19 @@ prompt = synth.synth_prompt(512, arch.vocab_size, arch.bos_token_id, 7)
 first = eng.prefill([prompt], [0], bt)
 eng.mega_profile(True)
 eng.decode_loop(first, [512], bt, 8)
-ids, ms = eng.decode_loop(first, [512], bt, 32)
+ids, ms = eng.decode_loop(first, [512], bt, 64)
 ns, types = eng.mega_profile(True)
-print("ms/token", ms / 32)
+n = len(types)
+ns = ns[:, :n].astype(np.int64)
+print("ms/token", ms / 64)
 names = ["qkv", "attn", "o", "gateup", "down", "lmhead"]
-t0 = ns[0, 0]
-work0 = ns[0, 1:] - ns[1, :-1]      # CTA0: phase start (prev barrier exit) -> phase end
-wait0 = ns[1, 1:] - ns[0, 1:]       # CTA0: barrier wait
-workL = ns[2, 1:] - ns[3, :-1]
-waitL = ns[3, 1:] - ns[2, 1:]
-print("token total us (cta0)", (ns[1, -1] - t0) / 1e3)
+print("token span us (cta0, first phase entry -> last phase end)", (ns[3, -1] - ns[0, 0]) / 1e3)
 for k in range(6):
     sel = types == k
-    print(f"{names[k]:7s} n={sel.sum():3d}  cta0 work {work0[sel].mean()/1e3:7.2f} wait {wait0[sel].mean()/1e3:6.2f} | ctaL work {workL[sel].mean()/1e3:7.2f} wait {waitL[sel].mean()/1e3:6.2f}  sum {(work0[sel].sum()+wait0[sel].sum())/1e3:8.1f} us")
-print("first 12 phases cta0 work/wait us:", [(names[types[i]], round(work0[i]/1e3,1), round(wait0[i]/1e3,1)) for i in range(12)])
+    if not sel.any():
+        continue
+    def avg(a):
+        return a[sel].mean() / 1e3
+    print(f"{names[k]:7s} n={sel.sum():3d} | cta0: barrier {avg(ns[1]-ns[0]):6.2f}  xload {avg(ns[2]-ns[1]):6.2f}  rows {avg(ns[3]-ns[2]):7.2f}"
+          f"  (weight-wait {ns[8][sel].mean()/1.965e3:6.2f}) | ctaL: barrier {avg(ns[5]-ns[4]):6.2f}  xload {avg(ns[6]-ns[5]):6.2f}  rows {avg(ns[7]-ns[6]):7.2f}"
+          f" | total {((ns[3]-ns[0])[sel].sum())/1e3:8.1f} us")
