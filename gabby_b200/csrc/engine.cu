@@ -381,6 +381,7 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     a.abort_flag = dev_abort;
     a.prof = c->mega_prof;
     a.debug_progress = std::getenv("B2L_MEGA_DEBUG") ? 1 : 0;
+    a.debug_nostream = std::getenv("B2L_MEGA_NOSTREAM") ? 1 : 0;
     a.max_inflight = c->mega_inflight;
     a.l2_ahead = c->mega_l2_ahead;
     B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));

@@ -67,6 +67,7 @@ struct MegaArgs {
     unsigned long long* bar_epoch;    // arrivals consumed by previous launches
     unsigned long long* argmax_keys;  // [3]
     int* abort_flag;     // mapped pinned host memory: [0] abort code, [1 + cta] progress marker of each CTA (debug)
+    int debug_nostream;  // 1: copy 16 bytes per chunk instead of the weights (timing experiments only; wrong results)
     int debug_progress;  // 1: CTAs record step*100000 + phase*100 + stage-of-phase
     int max_inflight;   // bulk copies issued but not yet landed, per CTA (bounds queueing latency in L2/HBM)
     int l2_ahead;       // chunks prefetched into L2 beyond the ring (0 = off)
@@ -850,6 +851,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const __gr
                 const uint16_t* src;
                 uint32_t bytes;
                 ld.get(src, bytes);
+                if (a.debug_nostream) bytes = 16;
                 mbar_arrive_expect_tx(sm.full + rp.stage * 8, bytes);
                 tma_bulk_g2s(sm.ring + static_cast<uint32_t>(rp.stage) * kMegaStageBytes, src, bytes, sm.full + rp.stage * 8, policy);
                 rp.advance(a.n_stages);
@@ -885,12 +887,20 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const __gr
                 const int item = blockIdx.x;
                 if (item < a.nkv * nsplit) {
                     const int kvh = item / nsplit, split = item % nsplit;
+#ifdef MEGA_ONLY_1B
+                    mega_attn_item<64, 4>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
+#else
                     if (a.hd == 64) mega_attn_group<64>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
                     else if (a.hd == 128) mega_attn_group<128>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
                     else mega_attn_group<32>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
+#endif
                 }
                 if (prof) a.prof[(prow + 3) * pstride + pi] = globaltimer_ns();
             } else {
+#ifdef MEGA_ONLY_1B
+                if (ph.ks == 1) mega_gemv_phase<8, false>(a, ph, sm, st, pi, pos, tid);
+                else mega_gemv_phase<8, true>(a, ph, sm, st, pi, pos, tid);
+#else
                 if (ph.ks == 1) {
                     switch (ph.m) {
                         case 1: mega_gemv_phase<1, false>(a, ph, sm, st, pi, pos, tid); break;
@@ -914,6 +924,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const __gr
                         default: mega_gemv_phase<8, true>(a, ph, sm, st, pi, pos, tid); break;
                     }
                 }
+#endif
             }
             if (ph.type == PH_LMHEAD) {
                 // CTA-level argmax, then one atomicMax per CTA on this step's key
