@@ -409,10 +409,10 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseReg
         }
     }
     if (ph.norm_w) {
-        float ss = 0.f;
+        float ssq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < M * 8; i++) ss = fmaf(xr[i], xr[i], ss);
-        ss = warp_sum(ss);
+        for (int i = 0; i < M * 8; i++) ssq[i & 3] = fmaf(xr[i], xr[i], ssq[i & 3]);
+        float ss = warp_sum((ssq[0] + ssq[1]) + (ssq[2] + ssq[3]));
         if (SPLIT) {  // a warp holds only its K slice: add the other slices' sums (warps 0..ks-1)
             if (lane == 0) sts32f(sm.red + w * 4, ss);
             consumer_bar();
@@ -465,9 +465,9 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseReg
             if (resid_h) resid = __ldcg(a.h + row_t);
             else if (resid_e) resid = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row_t]);
         }
-        float acc[kMegaRows][2];
+        float2 acc[kMegaRows];
 #pragma unroll
-        for (int t = 0; t < kMegaRows; t++) acc[t][0] = acc[t][1] = 0.f;
+        for (int t = 0; t < kMegaRows; t++) acc[t] = make_float2(0.f, 0.f);
         if (live) {
             uint32_t row_addr[kMegaRows];  // shared address of (row t, this warp's K slice, this lane)
             const int first_stage = rg * ks;
@@ -513,16 +513,12 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseReg
 #pragma unroll
                 for (int t = 0; t < kMegaRows; t++) {
                     const uint4 v = wv[i & 1][t];
-                    float sacc = acc[t][i & 1];
-                    sacc = fmaf(bf16lo(v.x), xr[i * 8 + 0], sacc);
-                    sacc = fmaf(bf16hi(v.x), xr[i * 8 + 1], sacc);
-                    sacc = fmaf(bf16lo(v.y), xr[i * 8 + 2], sacc);
-                    sacc = fmaf(bf16hi(v.y), xr[i * 8 + 3], sacc);
-                    sacc = fmaf(bf16lo(v.z), xr[i * 8 + 4], sacc);
-                    sacc = fmaf(bf16hi(v.z), xr[i * 8 + 5], sacc);
-                    sacc = fmaf(bf16lo(v.w), xr[i * 8 + 6], sacc);
-                    sacc = fmaf(bf16hi(v.w), xr[i * 8 + 7], sacc);
-                    acc[t][i & 1] = sacc;
+                    float2 s2 = acc[t];  // packed fp32x2 FMA (FFMA2): even elements in .x, odd in .y
+                    s2 = __ffma2_rn(make_float2(bf16lo(v.x), bf16hi(v.x)), make_float2(xr[i * 8 + 0], xr[i * 8 + 1]), s2);
+                    s2 = __ffma2_rn(make_float2(bf16lo(v.y), bf16hi(v.y)), make_float2(xr[i * 8 + 2], xr[i * 8 + 3]), s2);
+                    s2 = __ffma2_rn(make_float2(bf16lo(v.z), bf16hi(v.z)), make_float2(xr[i * 8 + 4], xr[i * 8 + 5]), s2);
+                    s2 = __ffma2_rn(make_float2(bf16lo(v.w), bf16hi(v.w)), make_float2(xr[i * 8 + 6], xr[i * 8 + 7]), s2);
+                    acc[t] = s2;
                 }
             }
             __syncwarp();
@@ -532,8 +528,11 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseReg
 #pragma unroll
                     for (int j = 0; j < kMegaRows; j++) {
                         if (j < ks && first_stage + j < n_stage_total) {
-                            mbar_arrive_n(sm.empty + rel.stage * 8, kMegaRows >> ks_shift);
+                            // publish "this use was read" BEFORE arriving: the stage can only be refilled (and
+                            // its next use released) after every arrival of this use, so the counter never runs
+                            // backwards (a late store after the arrive once did, and deadlocked a waiter)
                             asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sm.rel + rel.stage * 4), "r"(rel.use + 1) : "memory");
+                            mbar_arrive_n(sm.empty + rel.stage * 8, kMegaRows >> ks_shift);
                         }
                         rel.advance(n_stages);
                     }
@@ -543,7 +542,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseReg
         sp0 = sp0.plus(stage_step, n_stages);
         // transposed butterfly: 6 shuffles reduce all four rows; lane 8*t ends up with row t's sum.
         // Rows past the end of the range read a duplicate row; their sums are never stored.
-        const float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1], a2 = acc[2][0] + acc[2][1], a3 = acc[3][0] + acc[3][1];
+        const float a0 = acc[0].x + acc[0].y, a1 = acc[1].x + acc[1].y, a2 = acc[2].x + acc[2].y, a3 = acc[3].x + acc[3].y;
         float s0 = hi16 ? a2 : a0, s1 = hi16 ? a3 : a1;
         s0 += __shfl_xor_sync(0xffffffffu, hi16 ? a0 : a2, 16);
         s1 += __shfl_xor_sync(0xffffffffu, hi16 ? a1 : a3, 16);
