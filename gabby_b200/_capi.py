@@ -188,7 +188,7 @@ class Engine:
         """-> (ns [9][n_phases+1] uint64, phase_types [n_phases]) of the last megakernel token"""
         n = C.c_int(0)
         self._ck(self.L.b2l_debug_mega_profile(self.h, int(enable), None, C.byref(n), None), "mega_profile")
-        ns = np.zeros((9, n.value + 1), dtype=np.uint64)
+        ns = np.zeros((16, n.value + 1), dtype=np.uint64)
         types = np.zeros(n.value, dtype=np.int32)
         self._ck(self.L.b2l_debug_mega_profile(self.h, int(enable), _p(ns), C.byref(n), _p(types)), "mega_profile")
         return ns, types

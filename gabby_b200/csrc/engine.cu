@@ -355,8 +355,19 @@ void mega_setup(b2l_ctx* c) {
     B2L_CUDA(cudaMemset(c->mega_bar, 0, sizeof(unsigned long long) * 8));
     B2L_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->mega_abort), sizeof(int) * 1024, cudaHostAllocMapped));
     std::memset(c->mega_abort, 0, sizeof(int) * 1024);
+    {   // L2 persistence for the KV cache (B2L_MEGA_L2PERSIST=0 disables)
+        const char* e = std::getenv("B2L_MEGA_L2PERSIST");
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->p.device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->p.device);
+        size_t want = std::min<size_t>(static_cast<size_t>(c->kv_bytes), static_cast<size_t>(std::min(max_persist, max_window)));
+        if (e && std::atoi(e) == 0) want = 0;
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->mega_l2_persist_bytes = want;
+        else cudaGetLastError();
+    }
     if (const char* e = std::getenv("B2L_MEGA_INFLIGHT")) c->mega_inflight = std::atoi(e);   // tuning knobs
     if (const char* e = std::getenv("B2L_MEGA_L2AHEAD")) c->mega_l2_ahead = std::atoi(e);
+    if (const char* e = std::getenv("B2L_MEGA_ATTN_TPS")) c->mega_attn_tps = std::max(16, std::atoi(e));
     if (const char* e = std::getenv("B2L_MEGA_STAGES")) c->mega_stages = std::max(2, std::min(c->mega_stages, std::atoi(e)));
     c->mega_ok = true;
 }
@@ -383,6 +394,8 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     a.debug_progress = std::getenv("B2L_MEGA_DEBUG") ? 1 : 0;
     a.debug_nostream = std::getenv("B2L_MEGA_NOSTREAM") ? 1 : 0;
     a.max_inflight = c->mega_inflight;
+    a.attn_tps = c->mega_attn_tps;
+    a.producer_sleep_ns = std::getenv("B2L_MEGA_PSLEEP") ? std::atoi(std::getenv("B2L_MEGA_PSLEEP")) : 100;
     a.l2_ahead = c->mega_l2_ahead;
     B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));
     cudaLaunchConfig_t cfg{};
@@ -390,12 +403,23 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     cfg.blockDim = dim3(kMegaThreads);
     cfg.dynamicSmemBytes = c->mega_smem;
     cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel, a));
+    if (c->mega_l2_persist_bytes > 0) {
+        // keep the KV cache resident in the 126 MB L2 while 2.5 GB of weights stream past it every token
+        attr[1].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[1].val.accessPolicyWindow.base_ptr = c->kv_base;
+        attr[1].val.accessPolicyWindow.num_bytes = c->mega_l2_persist_bytes;
+        attr[1].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 2;
+    }
+    B2L_CUDA(cudaMemcpyToSymbolAsync(c_mega, &a, sizeof(MegaArgs), 0, cudaMemcpyHostToDevice, c->stream));
+    B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel));
     c->launched++;
 }
 
@@ -534,6 +558,9 @@ int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_
         c->final_norm = dalloc<uint16_t>(c, H);
         c->layers.resize(c->L);
         const size_t page_elems = static_cast<size_t>(2) * p->page_size * c->kvd_l;
+        // one allocation for every layer's KV pool: lets one L2 persisting window cover the whole cache
+        c->kv_base = dalloc<uint16_t>(c, page_elems * p->num_pages * c->L);
+        size_t kv_off = 0;
         for (auto& w : c->layers) {
             w.in_norm = dalloc<uint16_t>(c, H);
             w.post_norm = dalloc<uint16_t>(c, H);
@@ -541,7 +568,8 @@ int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_
             w.w_o = dalloc<uint16_t>(c, H * c->qd_l);
             w.w_gu = dalloc<uint16_t>(c, static_cast<size_t>(2) * c->I_l * H);
             w.w_down = dalloc<uint16_t>(c, H * c->I_l);
-            w.kv_pool = dalloc<uint16_t>(c, page_elems * p->num_pages);
+            w.kv_pool = c->kv_base + kv_off;
+            kv_off += page_elems * p->num_pages;
             c->weight_bytes += static_cast<int64_t>(2) * (2 * H + static_cast<size_t>(c->qkv_l) * H + H * c->qd_l + 3 * H * c->I_l);
             c->kv_bytes += static_cast<int64_t>(2) * page_elems * p->num_pages;
         }
@@ -857,7 +885,7 @@ int b2l_debug_mega_profile(b2l_ctx* c, int enable, uint64_t* out_ns, int* n_phas
     return guarded(c, [&] {
         require_ready(c);
         B2L_CHECK(c->mega_ok, "megakernel unavailable: " + c->mega_why);
-        const size_t n = 9 * static_cast<size_t>(c->mega_n_phases + 1);
+        const size_t n = 16 * static_cast<size_t>(c->mega_n_phases + 1);
         if (enable && !c->mega_prof) {
             c->mega_prof = dalloc<unsigned long long>(c, n);
             B2L_CUDA(cudaMemset(c->mega_prof, 0, n * 8));

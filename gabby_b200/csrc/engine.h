@@ -97,7 +97,9 @@ struct b2l_ctx {
     void* mega_phases = nullptr;     // device MegaPhase[]
     int mega_n_phases = 0, mega_stages = 0, mega_nsplit = 0;
     size_t mega_smem = 0;
-    int mega_inflight = 0, mega_l2_ahead = 0;
+    uint16_t* kv_base = nullptr;     // all layers' KV pools, contiguous
+    size_t mega_l2_persist_bytes = 0;
+    int mega_inflight = 0, mega_l2_ahead = 0, mega_attn_tps = 128;
     unsigned long long *mega_bar = nullptr;  // [0] counter, [1] epoch, [2..4] argmax keys
     int* mega_abort = nullptr;               // pinned host flag, device-visible
     unsigned long long* mega_prof = nullptr; // device [4][n_phases+1] phase timestamps (debug)

@@ -69,10 +69,17 @@ struct MegaArgs {
     int* abort_flag;     // mapped pinned host memory: [0] abort code, [1 + cta] progress marker of each CTA (debug)
     int debug_nostream;  // 1: copy 16 bytes per chunk instead of the weights (timing experiments only; wrong results)
     int debug_progress;  // 1: CTAs record step*100000 + phase*100 + stage-of-phase
+    int producer_sleep_ns;
+    int attn_tps;       // context tokens per attention split (work item)
     int max_inflight;   // bulk copies issued but not yet landed, per CTA (bounds queueing latency in L2/HBM)
     int l2_ahead;       // chunks prefetched into L2 beyond the ring (0 = off)
     unsigned long long* prof;  // optional [9][n_phases + 1], see b2l_debug_mega_profile globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
 };
+
+// The launch arguments live in __constant__ memory: the device functions below read them as
+// constant-bank operands (no reloads after inline-asm memory clobbers, no generic loads through a
+// pointer to the parameter space). One megakernel launch per device at a time (host side locks).
+__constant__ MegaArgs c_mega;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -187,7 +194,8 @@ __device__ __forceinline__ void mega_row_range(int N, int unit, int c, int G, in
 }
 
 // grid-wide barrier among the consumer threads of all CTAs: arrive (release) then wait for `target`
-__device__ __forceinline__ void mega_grid_sync(const MegaArgs& a, unsigned long long target, int tid) {
+__device__ __forceinline__ void mega_grid_sync(const MegaArgs& /*unused: c_mega*/, unsigned long long target, int tid) {
+    const MegaArgs& a = c_mega;
     consumer_bar();  // all of this CTA's writes are ordered before thread 0's release below
     if (tid == 0) {
         // release: cumulative over the CTA's writes ordered by the bar.sync above; readers use ld.global.cg
@@ -267,27 +275,59 @@ __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
 }
 
-__device__ __forceinline__ int mega_nsplit(int nsplit_max, int ctx) { return max(1, min(nsplit_max, (ctx + 127) >> 7)); }
+// Attention decomposition for this step. While (query heads x context splits) fits the grid, a work
+// item is one QUERY head x one split (4x shorter items than per-kv-head, K/V re-read from L2);
+// for longer contexts items are (kv head x split) and process the whole GQA group.
+struct AttnPlan {
+    int nsplit;
+    bool per_q_head;
+};
+__device__ __forceinline__ AttnPlan mega_attn_plan(int nsplit_max, int ctx, int tps, int nh, int G) {
+    AttnPlan p;
+    const int q_splits = min(nsplit_max, G / nh);          // splits per query head that still fit the grid
+    if (q_splits >= 1 && (ctx + q_splits - 1) / q_splits <= 2 * tps) {
+        p.per_q_head = true;                               // items of <= 2*tps tokens of ONE query head
+        p.nsplit = max(1, min(q_splits, (ctx + 31) / 32));
+    } else {
+        p.per_q_head = false;
+        p.nsplit = max(1, min(nsplit_max, (ctx + tps - 1) / tps));
+    }
+    return p;
+}
 
-// attention output elements [k, k+8) of this step: merge the split-K partials
-__device__ __forceinline__ void mega_attn_combine8(const MegaArgs& a, int k, int nsplit, float* out) {
+// attention output elements [k, k+8) of this step: merge the split-K partials.
+// Loads are issued four splits at a time (independent of each other), then merged online.
+__device__ __forceinline__ void mega_attn_combine8(const MegaArgs& /*unused: c_mega*/, int k, int nsplit, float* out) {
+    const MegaArgs& a = c_mega;
     const int head = k / a.hd, d = k % a.hd;  // 8 consecutive k never straddle a head (hd % 8 == 0)
     const int group = a.nh / a.nkv, kvh = head / group, g = head % group;
     const size_t rbase = static_cast<size_t>(kvh) * a.nsplit_max;
-    float Mx = -INFINITY;
-    for (int s = 0; s < nsplit; s++) Mx = fmaxf(Mx, __ldcg(a.part_ml + ((rbase + s) * group + g) * 2));
-    float L = 0.f, acc[8];
+    float Mx = -INFINITY, L = 0.f, acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
-    for (int s = 0; s < nsplit; s++) {
-        const float2 ml = __ldcg(reinterpret_cast<const float2*>(a.part_ml + ((rbase + s) * group + g) * 2));
-        if (ml.x == -INFINITY) continue;
-        const float wgt = __expf(ml.x - Mx);
-        L = fmaf(ml.y, wgt, L);
-        const float* pa = a.part_acc + ((rbase + s) * group + g) * a.hd + d;
-        const float4 p0 = __ldcg(reinterpret_cast<const float4*>(pa)), p1 = __ldcg(reinterpret_cast<const float4*>(pa + 4));
-        acc[0] = fmaf(p0.x, wgt, acc[0]); acc[1] = fmaf(p0.y, wgt, acc[1]); acc[2] = fmaf(p0.z, wgt, acc[2]); acc[3] = fmaf(p0.w, wgt, acc[3]);
-        acc[4] = fmaf(p1.x, wgt, acc[4]); acc[5] = fmaf(p1.y, wgt, acc[5]); acc[6] = fmaf(p1.z, wgt, acc[6]); acc[7] = fmaf(p1.w, wgt, acc[7]);
+    for (int s0 = 0; s0 < nsplit; s0 += 4) {
+        float2 ml[4];
+        float4 p0[4], p1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int s = min(s0 + u, nsplit - 1);  // clamped duplicates are masked below
+            ml[u] = __ldcg(reinterpret_cast<const float2*>(a.part_ml + ((rbase + s) * group + g) * 2));
+            const float* pa = a.part_acc + ((rbase + s) * group + g) * a.hd + d;
+            p0[u] = __ldcg(reinterpret_cast<const float4*>(pa));
+            p1[u] = __ldcg(reinterpret_cast<const float4*>(pa + 4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (s0 + u >= nsplit || ml[u].x == -INFINITY) continue;
+            const float mn = fmaxf(Mx, ml[u].x);
+            const float c_old = __expf(Mx - mn), c_new = __expf(ml[u].x - mn);  // exp(-inf) = 0 on the first split
+            L = L * c_old + ml[u].y * c_new;
+            acc[0] = acc[0] * c_old + p0[u].x * c_new; acc[1] = acc[1] * c_old + p0[u].y * c_new;
+            acc[2] = acc[2] * c_old + p0[u].z * c_new; acc[3] = acc[3] * c_old + p0[u].w * c_new;
+            acc[4] = acc[4] * c_old + p1[u].x * c_new; acc[5] = acc[5] * c_old + p1[u].y * c_new;
+            acc[6] = acc[6] * c_old + p1[u].z * c_new; acc[7] = acc[7] * c_old + p1[u].w * c_new;
+            Mx = mn;
+        }
     }
     const float inv = 1.0f / L;
 #pragma unroll
@@ -306,7 +346,8 @@ struct ConsumerState {
 
 // barrier that precedes a phase: wait for the previous phase's outputs; at a token boundary also
 // pick up the argmax that becomes the next input token
-__device__ __forceinline__ void mega_phase_barrier(const MegaArgs& a, ConsumerState& st, bool token_boundary, int tid) {
+__device__ __forceinline__ void mega_phase_barrier(const MegaArgs& /*unused: c_mega*/, ConsumerState& st, bool token_boundary, int tid) {
+    const MegaArgs& a = c_mega;
     if (!st.need_barrier) {
         st.need_barrier = true;
         return;
@@ -326,8 +367,9 @@ __device__ __forceinline__ void mega_phase_barrier(const MegaArgs& a, ConsumerSt
 #define MEGA_GEMV_ATTR __noinline__
 #endif
 template <int M, bool SPLIT>  // SPLIT: K is split over ks > 1 warps
-__device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseRegs ph, const MegaSmem sm, ConsumerState& st_ref,
+__device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs ph, const MegaSmem sm, ConsumerState& st_ref,
                                              int pi, int pos, int tid) {
+    const MegaArgs& a = c_mega;
     ConsumerState st = st_ref;  // work on a register copy; written back once at the end
     const int lane = tid & 31, w = tid >> 5;
     const int ks = SPLIT ? ph.ks : 1, slice = 256 * M;
@@ -356,7 +398,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseReg
 
     // ---- input vector -> registers (fused RMSNorm / split-K attention merge) ----
     const float* xsrc = type == PH_DOWN ? a.act : a.h;
-    const int nsplit = mega_nsplit(a.nsplit_max, pos + 1);
+    const int nsplit = mega_attn_plan(a.nsplit_max, pos + 1, a.attn_tps, a.nh, gridDim.x).nsplit;
     const int token = st.token;
     float xr[M * 8];
     if (!SPLIT) {
@@ -586,8 +628,12 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs& a, const PhaseReg
 
 // ---- attention work item: (kv head, split); partials are merged by the O-proj phase's x load -----
 template <int HD, int GROUP>
-__device__ __noinline__ void mega_attn_item(const MegaArgs& a, uint16_t* kv_pool, uint32_t scratch, int kvh, int split, int nsplit,
-                                            int pos, int tid) {
+__device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, uint32_t scratch, int kvh, int split, int nsplit,
+                                            int pos, int tid, unsigned long long* pcol, int group_total, int g0) {
+    // processes query heads kvh*group_total + g0 .. + GROUP (GROUP == group_total, or 1 in per-query-head mode)
+    const MegaArgs& a = c_mega;
+    long long ak0 = 0, ak1 = 0, ak2 = 0, ak3 = 0, ak4 = 0, ak5 = 0;
+    if (pcol) ak0 = clock64();
     constexpr int LPT = HD / 8, TPW = 32 / LPT, HALF = HD / 2;
     const int lane = tid & 31, w = tid >> 5, sub = lane / LPT, sl = lane % LPT;
     const KvLayout kv{kv_pool, a.page_size, a.kvd};
@@ -614,10 +660,11 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, uint16_t* kv_pool
     float q[GROUP][8];
 #pragma unroll
     for (int g = 0; g < GROUP; g++) {
-        rope_slice(a.qkv + (kvh * GROUP + g) * HD, q[g]);
+        rope_slice(a.qkv + (kvh * group_total + g0 + g) * HD, q[g]);
 #pragma unroll
         for (int i = 0; i < 8; i++) q[g][i] *= a.attn_scale;
     }
+    if (pcol) ak1 = clock64();
     float m[GROUP], l[GROUP], acc[GROUP][8];
 #pragma unroll
     for (int g = 0; g < GROUP; g++) {
@@ -626,48 +673,67 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, uint16_t* kv_pool
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
     }
-    for (int jb = j0; jb < j1; jb += kMegaConsumerWarps * TPW) {
-        const int j = jb + w * TPW + sub;
-        const bool valid = j < j1;
-        uint4 kw = make_uint4(0, 0, 0, 0), vw = make_uint4(0, 0, 0, 0);
-        if (valid) {
-            const int page = __ldg(a.block_table + j / a.page_size), off = j % a.page_size;
-            uint16_t* kp = kv.at(page, 0, off) + kvh * HD + sl * 8;
-            uint16_t* vp = kv.at(page, 1, off) + kvh * HD + sl * 8;
-            if (j == pos) {
-                // the token being decoded: K/V come from this step's projection; append them (bf16)
-                float kr[8];
-                rope_slice(a.qkv + qd + kvh * HD, kr);
-                const float* vsrc = a.qkv + qd + a.kvd + kvh * HD + sl * 8;
-                const float4 v0 = __ldcg(reinterpret_cast<const float4*>(vsrc)), v1 = __ldcg(reinterpret_cast<const float4*>(vsrc + 4));
-                kw = make_uint4(pack_bf16x2(kr[0], kr[1]), pack_bf16x2(kr[2], kr[3]), pack_bf16x2(kr[4], kr[5]), pack_bf16x2(kr[6], kr[7]));
-                vw = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
-                *reinterpret_cast<uint4*>(kp) = kw;
-                *reinterpret_cast<uint4*>(vp) = vw;
-            } else {
-                kw = __ldcg(reinterpret_cast<const uint4*>(kp));
-                vw = __ldcg(reinterpret_cast<const uint4*>(vp));
+    constexpr int U = 4;  // token slots per lane group in flight: all K/V loads of a block are issued before any math
+    for (int jb = j0; jb < j1; jb += U * kMegaConsumerWarps * TPW) {
+        uint4 kw[U], vw[U];
+        bool valid[U];
+        int page[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
+            valid[u] = j < j1;
+            page[u] = valid[u] ? __ldg(a.block_table + j / a.page_size) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
+            kw[u] = make_uint4(0, 0, 0, 0);
+            vw[u] = make_uint4(0, 0, 0, 0);
+            if (valid[u]) {
+                const int off = j % a.page_size;
+                uint16_t* kp = kv.at(page[u], 0, off) + kvh * HD + sl * 8;
+                uint16_t* vp = kv.at(page[u], 1, off) + kvh * HD + sl * 8;
+                if (j == pos) {
+                    // the token being decoded: K/V come from this step's projection; append them (bf16)
+                    float kr[8];
+                    rope_slice(a.qkv + qd + kvh * HD, kr);
+                    const float* vsrc = a.qkv + qd + a.kvd + kvh * HD + sl * 8;
+                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(vsrc)), v1 = __ldcg(reinterpret_cast<const float4*>(vsrc + 4));
+                    kw[u] = make_uint4(pack_bf16x2(kr[0], kr[1]), pack_bf16x2(kr[2], kr[3]), pack_bf16x2(kr[4], kr[5]), pack_bf16x2(kr[6], kr[7]));
+                    vw[u] = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+                    if (g0 == 0) {  // one writer per kv head
+                        *reinterpret_cast<uint4*>(kp) = kw[u];
+                        *reinterpret_cast<uint4*>(vp) = vw[u];
+                    }
+                } else {
+                    kw[u] = __ldcg(reinterpret_cast<const uint4*>(kp));
+                    vw[u] = __ldcg(reinterpret_cast<const uint4*>(vp));
+                }
             }
         }
-        const float kf[8] = {bf16lo(kw.x), bf16hi(kw.x), bf16lo(kw.y), bf16hi(kw.y), bf16lo(kw.z), bf16hi(kw.z), bf16lo(kw.w), bf16hi(kw.w)};
-        const float vf[8] = {bf16lo(vw.x), bf16hi(vw.x), bf16lo(vw.y), bf16hi(vw.y), bf16lo(vw.z), bf16hi(vw.z), bf16lo(vw.w), bf16hi(vw.w)};
 #pragma unroll
-        for (int g = 0; g < GROUP; g++) {
-            float s = 0.f;
+        for (int u = 0; u < U; u++) {
+            const float kf[8] = {bf16lo(kw[u].x), bf16hi(kw[u].x), bf16lo(kw[u].y), bf16hi(kw[u].y), bf16lo(kw[u].z), bf16hi(kw[u].z), bf16lo(kw[u].w), bf16hi(kw[u].w)};
+            const float vf[8] = {bf16lo(vw[u].x), bf16hi(vw[u].x), bf16lo(vw[u].y), bf16hi(vw[u].y), bf16lo(vw[u].z), bf16hi(vw[u].z), bf16lo(vw[u].w), bf16hi(vw[u].w)};
 #pragma unroll
-            for (int i = 0; i < 8; i++) s = fmaf(q[g][i], kf[i], s);
+            for (int g = 0; g < GROUP; g++) {
+                float s = 0.f;
 #pragma unroll
-            for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (valid) {
-                const float mn = fmaxf(m[g], s);
-                const float corr = __expf(m[g] - mn), p = __expf(s - mn);
-                l[g] = l[g] * corr + p;
+                for (int i = 0; i < 8; i++) s = fmaf(q[g][i], kf[i], s);
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[g][i] = fmaf(acc[g][i], corr, p * vf[i]);
-                m[g] = mn;
+                for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (valid[u]) {
+                    const float mn = fmaxf(m[g], s);
+                    const float corr = __expf(m[g] - mn), p = __expf(s - mn);
+                    l[g] = l[g] * corr + p;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[g][i] = fmaf(acc[g][i], corr, p * vf[i]);
+                    m[g] = mn;
+                }
             }
         }
     }
+    if (pcol) ak2 = clock64();
     // merge the TPW token sub-slots of the warp with shuffles
 #pragma unroll
     for (int o = LPT; o < 32; o <<= 1) {
@@ -685,6 +751,7 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, uint16_t* kv_pool
             m[g] = mn;
         }
     }
+    if (pcol) ak3 = clock64();
     // per-warp results -> smem: acc [w][g][HD], then (m, l) [w][g][2]
     const uint32_t s_acc = scratch, s_ml = scratch + kMegaConsumerWarps * GROUP * HD * 4;
     if (sub == 0) {
@@ -700,6 +767,7 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, uint16_t* kv_pool
         }
     }
     consumer_bar();
+    if (pcol) ak4 = clock64();
     const size_t pbase = static_cast<size_t>(kvh) * a.nsplit_max + split;
     for (int e = tid; e < GROUP * HD; e += kMegaConsumerThreads) {
         const int g = e / HD, d = e % HD;
@@ -715,23 +783,37 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs& a, uint16_t* kv_pool
                 A = fmaf(lds32f(s_acc + ((t * GROUP + g) * HD + d) * 4), wgt, A);
             }
         }
-        a.part_acc[(pbase * GROUP + g) * HD + d] = A;
+        a.part_acc[(pbase * group_total + g0 + g) * HD + d] = A;
         if (d == 0) {
-            a.part_ml[(pbase * GROUP + g) * 2] = Mx;
-            a.part_ml[(pbase * GROUP + g) * 2 + 1] = L;
+            a.part_ml[(pbase * group_total + g0 + g) * 2] = Mx;
+            a.part_ml[(pbase * group_total + g0 + g) * 2 + 1] = L;
         }
+    }
+    if (pcol) {
+        ak5 = clock64();
+        const int ps = a.n_phases + 1;
+        pcol[9 * ps] = ak1 - ak0;   // q rope
+        pcol[10 * ps] = ak2 - ak1;  // K/V loads + scores + online softmax
+        pcol[11 * ps] = ak3 - ak2;  // shuffle merge of sub-slots
+        pcol[12 * ps] = ak4 - ak3;  // smem + barrier
+        pcol[13 * ps] = ak5 - ak4;  // CTA merge + store
     }
 }
 
 template <int HD>
 __device__ __forceinline__ void mega_attn_group(const MegaArgs& a, uint16_t* kv_pool, uint32_t scratch, int kvh, int split,
-                                                int nsplit, int pos, int tid) {
-    switch (a.nh / a.nkv) {
-        case 1: mega_attn_item<HD, 1>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
-        case 2: mega_attn_item<HD, 2>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
-        case 3: mega_attn_item<HD, 3>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
-        case 4: mega_attn_item<HD, 4>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
-        default: mega_attn_item<HD, 8>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid); break;
+                                                int nsplit, int pos, int tid, unsigned long long* pcol, int g_only) {
+    const int group = a.nh / a.nkv;
+    if (g_only >= 0) {
+        mega_attn_item<HD, 1>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, group, g_only);
+        return;
+    }
+    switch (group) {
+        case 1: mega_attn_item<HD, 1>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 1, 0); break;
+        case 2: mega_attn_item<HD, 2>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 2, 0); break;
+        case 3: mega_attn_item<HD, 3>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 3, 0); break;
+        case 4: mega_attn_item<HD, 4>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 4, 0); break;
+        default: mega_attn_item<HD, 8>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 8, 0); break;
     }
 }
 
@@ -778,7 +860,8 @@ struct ChunkCursor {
     }
 };
 
-__global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const __grid_constant__ MegaArgs a) {
+__global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
+    const MegaArgs& a = c_mega;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     MegaSmem sm;
     sm.ring = smem_u32(smem_raw);
@@ -846,7 +929,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const __gr
                         outstanding--;
                     }
                 }
-                mbar_wait(sm.empty + rp.stage * 8, rp.parity ^ 1, a.abort_flag, 300);
+                if (!mbar_test_wait(sm.empty + rp.stage * 8, rp.parity ^ 1)) {
+                    // ring full: sleep between probes so the spinning producer does not steal issue slots
+                    // from the two consumer warps that share its scheduler
+                    unsigned spins = 0;
+                    while (!mbar_test_wait(sm.empty + rp.stage * 8, rp.parity ^ 1)) {
+                        __nanosleep(a.producer_sleep_ns);
+                        if (++spins > (1u << 26)) mega_die(a.abort_flag, 300);
+                    }
+                }
                 const uint16_t* src;
                 uint32_t bytes;
                 ld.get(src, bytes);
@@ -882,17 +973,18 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel(const __gr
                 if (prof) a.prof[(prow + 0) * pstride + pi] = globaltimer_ns();
                 mega_phase_barrier(a, st, false, tid);
                 if (prof) a.prof[(prow + 1) * pstride + pi] = a.prof[(prow + 2) * pstride + pi] = globaltimer_ns();
-                const int nsplit = mega_nsplit(a.nsplit_max, pos + 1);
-                const int item = blockIdx.x;
-                if (item < a.nkv * nsplit) {
-                    const int kvh = item / nsplit, split = item % nsplit;
-#ifdef MEGA_ONLY_1B
-                    mega_attn_item<64, 4>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
-#else
-                    if (a.hd == 64) mega_attn_group<64>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
-                    else if (a.hd == 128) mega_attn_group<128>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
-                    else mega_attn_group<32>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid);
-#endif
+                const AttnPlan plan = mega_attn_plan(a.nsplit_max, pos + 1, a.attn_tps, a.nh, gridDim.x);
+                const int nsplit = plan.nsplit, item = blockIdx.x;
+                const int n_items = (plan.per_q_head ? a.nh : a.nkv) * nsplit;
+                if (item < n_items) {
+                    const int unit = item / nsplit, split = item % nsplit;   // query head or kv head
+                    const int group = a.nh / a.nkv;
+                    const int kvh = plan.per_q_head ? unit / group : unit;
+                    const int g_only = plan.per_q_head ? unit % group : -1;
+                    unsigned long long* pcol = prof && blockIdx.x == 0 ? a.prof + pi : nullptr;
+                    if (a.hd == 64) mega_attn_group<64>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only);
+                    else if (a.hd == 128) mega_attn_group<128>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only);
+                    else mega_attn_group<32>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only);
                 }
                 if (prof) a.prof[(prow + 3) * pstride + pi] = globaltimer_ns();
             } else {

@@ -28,3 +28,7 @@ for k in range(6):
     print(f"{names[k]:7s} n={sel.sum():3d} | cta0: barrier {avg(ns[1]-ns[0]):6.2f}  xload {avg(ns[2]-ns[1]):6.2f}  rows {avg(ns[3]-ns[2]):7.2f}"
           f"  (weight-wait {ns[8][sel].mean()/1.965e3:6.2f}) | ctaL: barrier {avg(ns[5]-ns[4]):6.2f}  xload {avg(ns[6]-ns[5]):6.2f}  rows {avg(ns[7]-ns[6]):7.2f}"
           f" | total {((ns[3]-ns[0])[sel].sum())/1e3:8.1f} us")
+
+sel = types == 1
+print("attention item breakdown, cta0 tid0 (us): q-rope / loads+scores / sub-slot merge / smem+barrier / CTA merge+store")
+print(" ".join(f"{ns[r][sel].mean()/1.965e3:6.2f}" for r in (9, 10, 11, 12, 13)))
