@@ -1,10 +1,11 @@
 /*
  * gabby_b200_host.h -- C view of the host C++ layer (gabby_b200/host/), for callers that cannot
  * include C++ headers (tests, bench.py). The C++ interface itself mirrors gabby's:
- * gabby::inference::{Message, Request, Generator, Llama3Generator::Load}
- * (/root/reference/src/inference/generator.h:16-47) -- see gabby_b200/host/generator.h.
+ * gabby::inference::{Message, Request, Generator, Llama3Generator::Load, InferenceConfig, LoadConfig,
+ * Safetensors, Tokenizer} (/root/reference/src/inference/*.h) -- see gabby_b200/host/generator.h.
  *
- * All functions return 0 on success; gb_last_error() holds the message otherwise.
+ * All int functions return 0 on success; gb_last_error() holds the message otherwise (the text of
+ * the C++ exception: what gabby's server would turn into HTTP 400/500, src/http/server.cc:371-378).
  */
 #ifndef GABBY_B200_HOST_H_
 #define GABBY_B200_HOST_H_
@@ -21,6 +22,56 @@ const char* gb_last_error(void);
  * rope_theta / rope_scaling (llama3 != 0: apply the llama3 band rescaling). */
 int gb_rope_table(double rope_theta, int llama3, double factor, double low_freq_factor, double high_freq_factor,
                   int original_max_position, int head_dim, int max_pos, float* out);
+
+/* ---- Llama3Generator (generator.h) ---- */
+typedef struct gb_generator gb_generator;
+/* LoadConfig(model_dir) + Llama3Generator::Load: parses the JSON files, maps the safetensors
+ * (single file or sharded), uploads every tensor, sizes the paged KV pool. */
+int gb_generator_load(const char* model_dir, int device, int max_positions, int max_new_tokens, gb_generator** out);
+void gb_generator_free(gb_generator* g);
+/* Generator::Generate(Request{system, user}) -> Message.content (NUL-terminated, truncated to cap) */
+int gb_generator_generate(gb_generator* g, const char* system_text, const char* user_text, char* out, int cap);
+/* token-level: prefill `prompt` then greedy decode; finish: 1 = EOS ("stop"), 2 = max_new_tokens ("length") */
+int gb_generator_generate_ids(gb_generator* g, const int32_t* prompt, int n_prompt, int max_new_tokens, int device_loop,
+                              int32_t* out_ids, int* n_out, int* finish);
+void* gb_generator_engine(gb_generator* g); /* the b2l_ctx* behind it (parity taps) */
+
+/* ---- pieces, exposed for CPU-side tests ---- */
+typedef struct {
+    int32_t hidden_size, intermediate_size, num_hidden_layers, num_attention_heads, num_key_value_heads, head_dim, vocab_size;
+    int32_t tie_word_embeddings, max_position_embeddings, bos_token_id, n_eos, eos_token_ids[8];
+    int32_t rope_llama3, rope_original_max_position;
+    float rms_norm_eps;
+    double rope_theta, rope_factor, rope_low_freq_factor, rope_high_freq_factor;
+} gb_params;
+int gb_params_from_dir(const char* model_dir, gb_params* out);                 /* ParamsFromConfig(LoadConfig(dir)) */
+int gb_params_from_json(const char* config_json, const char* gen_json, gb_params* out);
+
+/* Checkpoint accessor: number of tensors / files, and one tensor's metadata + a 64-bit FNV-1a of its bytes */
+int gb_checkpoint_info(const char* model_dir, int* n_tensors, int* n_files);
+int gb_checkpoint_tensor(const char* model_dir, const char* name, int64_t* shape4, int* ndim, char* dtype8, uint64_t* nbytes,
+                         uint64_t* fnv1a64);
+
+/* KvPageAllocator */
+typedef struct gb_kv gb_kv;
+int gb_kv_create(int num_pages, int page_size, int max_blocks, gb_kv** out);
+void gb_kv_free(gb_kv* kv);
+int gb_kv_new_sequence(gb_kv* kv, int* seq);
+int gb_kv_reserve(gb_kv* kv, int seq, int total_tokens);
+int gb_kv_release(gb_kv* kv, int seq);
+int gb_kv_table(gb_kv* kv, int seq, int32_t* out, int cap, int* n_blocks);
+int gb_kv_free_pages(gb_kv* kv);
+
+/* Tokenizer built from a tokenizer.json text (NULL/"" = byte fallback) */
+typedef struct gb_tokenizer gb_tokenizer;
+int gb_tokenizer_create(const char* tokenizer_json, gb_tokenizer** out);
+void gb_tokenizer_free(gb_tokenizer* t);
+int gb_tokenize(gb_tokenizer* t, const char* text, int32_t* out, int cap, int* n);
+int gb_detokenize(gb_tokenizer* t, const int32_t* ids, int n, char* out, int cap);
+int gb_chat_prompt(gb_tokenizer* t, const char* system_text, const char* user_text, int32_t* out, int cap, int* n);
+
+/* GreedySampler::Argmax (first max) on host logits */
+int32_t gb_argmax(const float* logits, int64_t n);
 
 #ifdef __cplusplus
 }
