@@ -106,7 +106,7 @@ class Engine:
                                 int(arch.tie_word_embeddings), arch.rms_norm_eps, max_batch, max_positions, page_size,
                                 num_pages, max_prefill_tokens, tp_rank, tp_size, device)
         h = C.c_void_p()
-        idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id else None
+        idbuf = (C.c_char * 128).from_buffer_copy(nccl_id) if nccl_id else None
         if self.L.b2l_create(C.byref(self.params), _p(rope), idbuf, C.byref(h)) != 0:
             raise B2lError("b2l_create: " + self.L.b2l_last_error(None).decode())
         self.h = h
@@ -206,6 +206,14 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL unique id (rank 0 makes it, every TP rank passes it to Engine(nccl_id=...))."""
+    buf = C.create_string_buffer(128)
+    if lib().b2l_nccl_unique_id(buf) != 0:
+        raise B2lError("b2l_nccl_unique_id: " + lib().b2l_last_error(None).decode())
+    return buf.raw
 
 
 def op_gemv(W_bits, x, y_in=None, norm_w_bits=None, eps=1e-5, mode=0, iters=1, device=0):

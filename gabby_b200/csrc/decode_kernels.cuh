@@ -427,6 +427,31 @@ __global__ void add_kernel(float* __restrict__ y, const float* __restrict__ x, i
     if (i < n) y[i] += x[i];
 }
 
+// TP greedy argmax: pack this rank's (max value, global index) per row for the all-gather ...
+__global__ void tp_pack_kernel(const float* __restrict__ vals, const int32_t* __restrict__ ids, float* __restrict__ pack, int R) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = threadIdx.x;
+    if (r < R) {
+        pack[2 * r] = vals[r];
+        pack[2 * r + 1] = static_cast<float>(ids[r]);   // < 2^24: exact in fp32
+    }
+}
+// ... and pick the winner over ranks (ties -> lowest index = first max, like the single-GPU kernel)
+__global__ void tp_merge_kernel(const float* __restrict__ gathered, int32_t* __restrict__ ids, int R, int stride_rows, int tp) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = threadIdx.x;
+    if (r >= R) return;
+    unsigned long long best = 0ull;
+    for (int k = 0; k < tp; k++) {
+        const float* p = gathered + (static_cast<size_t>(k) * stride_rows + r) * 2;
+        const unsigned long long key = argmax_key(p[0], static_cast<int>(p[1]));
+        best = key > best ? key : best;
+    }
+    ids[r] = argmax_key_index(best);
+}
+
 // standalone RMSNorm (parity tap of the final norm only; the hot path fuses it into the GEMV)
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const uint16_t* __restrict__ w, float* __restrict__ y,
                                int H, float eps) {

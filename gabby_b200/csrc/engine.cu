@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
 #include <functional>
 
 #include "decode_kernels.cuh"
@@ -21,6 +22,50 @@ using namespace b2l;
 namespace {
 
 thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen: no link-time dependency, and when the caller already loaded a libnccl.so.2
+// (torch ships one) the same copy is reused. Only the handful of entry points TP decode needs. ----
+struct NcclApi {
+    using Id = struct { char internal[B2L_NCCL_ID_BYTES]; };
+    int (*GetUniqueId)(Id*) = nullptr;
+    int (*CommInitRank)(void**, int, Id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+constexpr int kNcclFloat32 = 7, kNcclSum = 0;
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        api.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return api;
+    }
+    auto sym = [&](const char* n) { return dlsym(h, n); };
+    api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.GetErrorString;
+    if (!api.ok) api.why = "libnccl.so.2 lacks an expected symbol";
+    return api;
+}
+
+#define B2L_NCCL(expr)                                                                             \
+    do {                                                                                           \
+        int _r = (expr);                                                                           \
+        if (_r != 0) throw ::b2l::Error(std::string(#expr) + ": " + nccl().GetErrorString(_r));   \
+    } while (0)
 
 // ---- tensor naming (HF names as they appear in the safetensors header) --------------------
 enum Kind { K_EMBED, K_FINAL_NORM, K_LM_HEAD, K_IN_NORM, K_Q, K_K, K_V, K_O, K_POST_NORM, K_GATE, K_UP, K_DOWN, K_BAD };
@@ -205,6 +250,25 @@ void tap_copy(b2l_ctx* c, int slab, int row0, const float* src, int R) {
     B2L_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * R * c->H, cudaMemcpyDeviceToDevice, c->stream));
 }
 
+// h += all_reduce_sum(proj) over the TP ranks (fp32; the messages are R x H x 4 bytes: latency-bound)
+void tp_allreduce_add(b2l_ctx* c, int R) {
+    const size_t n = static_cast<size_t>(R) * c->H;
+    B2L_NCCL(nccl().AllReduce(c->proj, c->proj, n, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream));
+    launch(c, add_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, c->h, static_cast<const float*>(c->proj), static_cast<int>(n));
+}
+
+// greedy argmax over vocab-sharded logits: local (max, global index), all-gather, first-max merge
+void tp_argmax(b2l_ctx* c, const float* logits, int R) {
+    if (c->p.tp_size == 1) {
+        launch(c, argmax_kernel, dim3(R), dim3(1024), 0, logits, c->V_l, c->V_l, 0, c->d_next_ids, static_cast<float*>(nullptr));
+        return;
+    }
+    launch(c, argmax_kernel, dim3(R), dim3(1024), 0, logits, c->V_l, c->V_l, c->p.tp_rank * c->V_l, c->d_next_ids, c->tp_vals);
+    launch(c, tp_pack_kernel, dim3(1), dim3(64), 0, static_cast<const float*>(c->tp_vals), static_cast<const int32_t*>(c->d_next_ids), c->tp_pack, R);
+    B2L_NCCL(nccl().AllGather(c->tp_pack, c->tp_gather, static_cast<size_t>(c->max_rows) * 2, kNcclFloat32, c->nccl_comm, c->stream));
+    launch(c, tp_merge_kernel, dim3(1), dim3(64), 0, static_cast<const float*>(c->tp_gather), c->d_next_ids, R, c->max_rows, c->p.tp_size);
+}
+
 // The forward pass for R rows whose (token, position, slot) are already in device buffers.
 //   want_logits: run final norm + lm_head + argmax;  tap_row0 >= 0: record the residual stream.
 void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
@@ -219,9 +283,20 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
         const AttnArgs aa{c->qkv, c->qkv_l, kv, rm, c->part_acc, c->part_ml, c->attn_counters, c->attn, c->qd_l, scale};
         attn_launch(c, aa, R);
-        gemv(c, w.w_o, c->attn, c->qd_l, c->h, c->H, nullptr, c->H, c->qd_l, 1, R);
+        if (c->p.tp_size == 1) {
+            gemv(c, w.w_o, c->attn, c->qd_l, c->h, c->H, nullptr, c->H, c->qd_l, 1, R);
+        } else {
+            // row-parallel O: every rank holds a K slice, the partial products are summed over NVLink
+            gemv(c, w.w_o, c->attn, c->qd_l, c->proj, c->H, nullptr, c->H, c->qd_l, 0, R);
+            tp_allreduce_add(c, R);
+        }
         gemv(c, w.w_gu, c->h, c->H, c->act, c->I_l, w.post_norm, 2 * c->I_l, c->H, 2, R);
-        gemv(c, w.w_down, c->act, c->I_l, c->h, c->H, nullptr, c->H, c->I_l, 1, R);
+        if (c->p.tp_size == 1) {
+            gemv(c, w.w_down, c->act, c->I_l, c->h, c->H, nullptr, c->H, c->I_l, 1, R);
+        } else {
+            gemv(c, w.w_down, c->act, c->I_l, c->proj, c->H, nullptr, c->H, c->I_l, 0, R);
+            tp_allreduce_add(c, R);
+        }
         if (tap_row0 >= 0) tap_copy(c, l + 1, tap_row0, c->h, R);
     }
     if (tap_row0 >= 0) {
@@ -231,8 +306,7 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
     }
     if (want_logits) {
         gemv(c, c->lm_head, c->h, c->H, c->logits, c->V_l, c->final_norm, c->V_l, c->H, 0, R);
-        launch(c, argmax_kernel, dim3(R), dim3(1024), 0, static_cast<const float*>(c->logits), c->V_l, c->V_l,
-               c->p.tp_rank * c->V_l, c->d_next_ids, static_cast<float*>(nullptr));
+        tp_argmax(c, c->logits, R);
     }
 }
 
@@ -499,9 +573,17 @@ extern "C" {
 const char* b2l_last_error(const b2l_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
 int b2l_nccl_unique_id(void* out_bytes) {
-    (void)out_bytes;
-    g_create_error = "tensor parallelism is not built into this library yet";
-    return 1;
+    try {
+        B2L_CHECK(out_bytes, "null argument");
+        B2L_CHECK(nccl().ok, nccl().why);
+        NcclApi::Id id;
+        B2L_NCCL(nccl().GetUniqueId(&id));
+        std::memcpy(out_bytes, id.internal, B2L_NCCL_ID_BYTES);
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return 1;
+    }
 }
 
 int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_unique_id, b2l_ctx** out) {
@@ -515,7 +597,6 @@ int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_
         B2L_CHECK(p->device >= 0 && p->device < ndev, "device ordinal out of range");
         B2L_CHECK(p->tp_size >= 1 && p->tp_rank >= 0 && p->tp_rank < p->tp_size, "bad tp_rank / tp_size");
         B2L_CHECK(p->tp_size == 1 || nccl_unique_id, "tp_size > 1 needs an NCCL unique id");
-        B2L_CHECK(p->tp_size == 1, "tensor parallelism is not built into this library yet");
         B2L_CHECK(p->head_dim == 32 || p->head_dim == 64 || p->head_dim == 128, "head_dim must be 32, 64 or 128");
         B2L_CHECK(p->num_heads % p->num_kv_heads == 0, "num_heads must be a multiple of num_kv_heads");
         B2L_CHECK(p->num_kv_heads % p->tp_size == 0 && p->intermediate_size % p->tp_size == 0 && p->vocab_size % p->tp_size == 0,
@@ -601,6 +682,15 @@ int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_
         B2L_CUDA(cudaMemset(c->qkv, 0, sizeof(float) * R * c->qkv_l));
         B2L_CUDA(cudaMemset(c->attn, 0, sizeof(float) * R * c->qd_l));
         B2L_CUDA(cudaMemset(c->act, 0, sizeof(float) * R * c->I_l));
+        if (tp > 1) {
+            B2L_CHECK(nccl().ok, nccl().why);
+            c->tp_pack = dalloc<float>(c, static_cast<size_t>(R) * 2);
+            c->tp_gather = dalloc<float>(c, static_cast<size_t>(R) * 2 * tp);
+            c->tp_vals = dalloc<float>(c, R);
+            NcclApi::Id id;
+            std::memcpy(id.internal, nccl_unique_id, B2L_NCCL_ID_BYTES);
+            B2L_NCCL(nccl().CommInitRank(&c->nccl_comm, tp, id, p->tp_rank));   // collective: every rank is in b2l_create now
+        }
         B2L_CUDA(cudaDeviceSynchronize());
         *out = c;
         return 0;
@@ -620,6 +710,7 @@ void b2l_destroy(b2l_ctx* c) {
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
     }
+    if (c->nccl_comm) nccl().CommDestroy(c->nccl_comm);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->mega_abort) cudaFreeHost(c->mega_abort);
@@ -806,8 +897,7 @@ int b2l_prefill(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* q_l
             }
             tok0 += q_lens[i];
         }
-        launch(c, argmax_kernel, dim3(n_seq), dim3(1024), 0, static_cast<const float*>(c->seq_logits), c->V_l, c->V_l,
-               c->p.tp_rank * c->V_l, c->d_next_ids, static_cast<float*>(nullptr));
+        tp_argmax(c, c->seq_logits, n_seq);
         int32_t* h_next = c->h_stage + 3 * c->max_rows + static_cast<size_t>(c->p.max_batch) * c->max_blocks_cap;
         B2L_CUDA(cudaMemcpyAsync(h_next, c->d_next_ids, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, c->stream));
         B2L_CUDA(cudaStreamSynchronize(c->stream));
@@ -823,8 +913,23 @@ int b2l_get_logits(b2l_ctx* c, int row0, int n_rows, float* out) {
         B2L_CHECK(out && c->logits_src, "no logits available (run prefill or decode first)");
         B2L_CHECK(row0 >= 0 && n_rows >= 1 && row0 + n_rows <= c->logits_rows, "logit rows out of range");
         B2L_CUDA(cudaStreamSynchronize(c->stream));
-        B2L_CUDA(cudaMemcpy(out, c->logits_src + static_cast<size_t>(row0) * c->V_l, sizeof(float) * n_rows * c->V_l,
-                            cudaMemcpyDeviceToHost));
+        if (c->p.tp_size == 1) {
+            B2L_CUDA(cudaMemcpy(out, c->logits_src + static_cast<size_t>(row0) * c->V_l, sizeof(float) * n_rows * c->V_l,
+                                cudaMemcpyDeviceToHost));
+        } else {
+            // collective: every rank calls b2l_get_logits with the same rows; vocab shards are gathered
+            const int tp = c->p.tp_size;
+            const size_t shard = static_cast<size_t>(n_rows) * c->V_l;
+            if (!c->tp_logits) c->tp_logits = dalloc<float>(c, static_cast<size_t>(std::max(c->max_rows, c->p.max_batch)) * c->V_l * tp);
+            B2L_NCCL(nccl().AllGather(c->logits_src + static_cast<size_t>(row0) * c->V_l, c->tp_logits, shard, kNcclFloat32, c->nccl_comm, c->stream));
+            B2L_CUDA(cudaStreamSynchronize(c->stream));
+            std::vector<float> tmp(shard * tp);
+            B2L_CUDA(cudaMemcpy(tmp.data(), c->tp_logits, sizeof(float) * shard * tp, cudaMemcpyDeviceToHost));
+            for (int r = 0; r < tp; r++)
+                for (int row = 0; row < n_rows; row++)
+                    std::memcpy(out + static_cast<size_t>(row) * c->V + static_cast<size_t>(r) * c->V_l,
+                                tmp.data() + (static_cast<size_t>(r) * n_rows + row) * c->V_l, sizeof(float) * c->V_l);
+        }
     });
 }
 

@@ -104,6 +104,13 @@ struct b2l_ctx {
     int* mega_abort = nullptr;               // pinned host flag, device-visible
     unsigned long long* mega_prof = nullptr; // device [4][n_phases+1] phase timestamps (debug)
 
+    // tensor parallelism (NCCL, loaded with dlopen only when tp_size > 1)
+    void* nccl_comm = nullptr;
+    float* tp_pack = nullptr;        // [max_rows][2]   (value, index) of this rank's argmax
+    float* tp_gather = nullptr;      // [tp][max_rows][2]
+    float* tp_logits = nullptr;      // [tp][rows][V_l] gather buffer for b2l_get_logits (lazy)
+    float* tp_vals = nullptr;        // [max_rows] local max values
+
     std::map<int, b2l::Graph> decode_graphs;  // key: rows (+ 1000 when the loop variant with advance)
     int64_t launched = 0;
 
