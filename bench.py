@@ -153,6 +153,97 @@ def build_engine(arch, device: int, max_positions: int):
     return eng
 
 
+def run_8b_tp(args):
+    """BASELINE configs[3]: Llama-3.1-8B bf16, tensor-parallel over the N ranks torchrun started (strong
+    scaling: the model is fixed, every rank streams 1/N of it), batch-B decode from a 4K context, NCCL
+    all-reduce after the attention output projection and the MLP down projection. Weights are generated
+    on-device; the KV cache is synthetic (zeros) -- timing only, parity is covered by tests/test_gpu_tp.py."""
+    import torch
+    import torch.distributed as dist
+    from gabby_b200 import _capi, _host, synth
+    rank, world, local = dist_env()
+    K, W, B, ctx0 = args.steps, max(3, args.warmup), args.batch, args.context
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0 and world > 1:
+        idt.copy_(torch.frombuffer(bytearray(_capi.nccl_unique_id()), dtype=torch.uint8))
+    if world > 1:
+        dist.broadcast(idt, 0)
+    nccl_id = bytes(idt.cpu().numpy().tobytes()) if world > 1 else None
+    arch = synth.preset("8b")
+    max_positions = ctx0 + 2 * (K + W) + 64
+    eng = _capi.Engine(arch, _host.rope_table(arch, max_positions), max_batch=B, max_positions=max_positions, page_size=PAGE,
+                       max_prefill_tokens=64, device=local, tp_rank=rank, tp_size=world, nccl_id=nccl_id)
+    for name, shape, scale, off in synth.tensor_specs(arch):
+        eng.synth(name, shape, synth.tensor_seed(name, SEED), scale, off)
+    eng.finalize()
+    info = eng.info()
+    bt = np.arange(B * eng.max_blocks, dtype=np.int32).reshape(B, eng.max_blocks)
+    tok = synth.synth_prompt(B + 1, arch.vocab_size, arch.bos_token_id, SEED + 2)[1:]
+    pos = [ctx0] * B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng.decode_loop(tok, pos, bt, W)
+    barrier()
+    l0 = eng.info().kernels_launched
+    with ClockSampler(local) as clk:
+        ids, dev_ms = eng.decode_loop(tok, pos, bt, K)
+        reps, extra = 0, 0.0
+        while dev_ms + extra < 1500.0 and reps < 16:
+            _, m = eng.decode_loop(tok, pos, bt, K)
+            extra += m; reps += 1
+    launches = (eng.info().kernels_launched - l0) // (1 + reps)
+    barrier()
+    t = torch.tensor([dev_ms], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / K
+    value = B * 1000.0 / ms_per_step
+    # e2e: per-step C-ABI calls with host buffers
+    cur, p = tok.copy(), list(pos)
+    for _ in range(W):
+        cur = eng.decode(cur, p, bt); p = [x + 1 for x in p]
+    barrier()
+    cur, p = tok.copy(), list(pos)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        cur = eng.decode(cur, p, bt); p = [x + 1 for x in p]
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = B * K / float(t.item())
+    kv_per_tok = 2 * arch.num_hidden_layers * (arch.num_key_value_heads // world) * arch.head_dim * 2
+    bytes_per_step = info.stream_bytes_per_token + B * ((ctx0 + K / 2.0) * kv_per_tok + kv_per_tok)   # per GPU
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"llama-3.1-8b bf16 tensor-parallel decode, batch {B}, context {ctx0} (BASELINE configs[3])",
+                       "batch": B, "context": [ctx0, ctx0 + K], "parallelism": f"tp{world}", "kv": "paged bf16 (synthetic zeros), page 16",
+                       "collective": "ncclAllReduce fp32 sum after O-proj and down-proj (64 per token) + (value,index) all-gather for argmax",
+                       "l2": "inputs larger than L2", "decode_mode": 0},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "bytes_per_step_per_gpu": bytes_per_step,
+                         "kernel": f"decode step = CUDA graph of {launches // K} kernels + NCCL; per-GPU fraction"},
+            "cpu_baseline": None,
+            "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": B * (12 + 4 * eng.max_blocks), "d2h_bytes_per_step": 4 * B},
+            "gpu_launches": int(launches), "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,10 +252,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-mode", type=int, default=None)
+    ap.add_argument("--workload", default="1b-decode", choices=["1b-decode", "8b-tp"],
+                    help="1b-decode: BASELINE configs[1], N replicas (default). 8b-tp: configs[3], Llama-3.1-8B tensor-parallel over N GPUs")
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--context", type=int, default=4096)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    if args.workload == "8b-tp":
+        return run_8b_tp(args)
     rank, world, local = dist_env()
     K, W = args.steps, max(3, args.warmup)
     import torch

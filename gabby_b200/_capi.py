@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(PKG, "libb2l.so")
 
 # every symbol include/b2l.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
-    "b2l_create", "b2l_nccl_unique_id", "b2l_upload_tensor", "b2l_synth_tensor", "b2l_finalize", "b2l_destroy",
+    "b2l_create", "b2l_nccl_unique_id", "b2l_shard_window", "b2l_upload_tensor", "b2l_synth_tensor", "b2l_finalize", "b2l_destroy",
     "b2l_prefill", "b2l_decode", "b2l_decode_loop", "b2l_get_logits", "b2l_set_taps", "b2l_get_hidden",
     "b2l_get_kv_page", "b2l_get_info", "b2l_set_decode_mode", "b2l_debug_mega_profile", "b2l_last_error", "b2l_op_gemv", "b2l_op_argmax",
 ]
@@ -59,6 +59,7 @@ def lib():
     L.b2l_nccl_unique_id.argtypes = [vp]
     L.b2l_upload_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_int64), C.c_int]
     L.b2l_synth_tensor.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64), C.c_int, C.c_uint32, C.c_float, C.c_float]
+    L.b2l_shard_window.argtypes = [C.POINTER(B2lParams), C.c_char_p, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int64)]
     L.b2l_finalize.argtypes = [vp]
     L.b2l_destroy.argtypes = [vp]
     L.b2l_destroy.restype = None
@@ -206,6 +207,18 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+
+def shard_window(arch, name: str, shape, tp_rank: int, tp_size: int):
+    """(row0, nrows, col0, ncols) of the full HF tensor that `tp_rank` keeps. No GPU needed."""
+    p = B2lParams(arch.hidden_size, arch.intermediate_size, arch.num_hidden_layers, arch.num_attention_heads,
+                  arch.num_key_value_heads, arch.head_dim, arch.vocab_size, int(arch.tie_word_embeddings), arch.rms_norm_eps,
+                  1, 64, 16, 4, 64, tp_rank, tp_size, 0)
+    sh = (C.c_int64 * len(shape))(*shape)
+    win = (C.c_int64 * 4)()
+    if lib().b2l_shard_window(C.byref(p), name.encode(), sh, len(shape), win) != 0:
+        raise B2lError("b2l_shard_window: " + lib().b2l_last_error(None).decode())
+    return tuple(win)
 
 
 def nccl_unique_id() -> bytes:

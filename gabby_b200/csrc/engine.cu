@@ -759,6 +759,31 @@ int b2l_synth_tensor(b2l_ctx* c, const char* hf_name, const int64_t* shape, int 
     });
 }
 
+int b2l_shard_window(const b2l_params* p, const char* hf_name, const int64_t* shape, int ndim, int64_t win[4]) {
+    try {
+        B2L_CHECK(p && hf_name && shape && win, "null argument");
+        B2L_CHECK(p->tp_size >= 1 && p->tp_rank >= 0 && p->tp_rank < p->tp_size, "bad tp_rank / tp_size");
+        B2L_CHECK(p->num_kv_heads % p->tp_size == 0 && p->intermediate_size % p->tp_size == 0 && p->vocab_size % p->tp_size == 0,
+                  "kv heads, intermediate size and vocab must divide by tp_size");
+        b2l_ctx c;   // dims only; no device state is touched
+        c.p = *p;
+        const int tp = p->tp_size;
+        c.H = p->hidden_size; c.L = p->num_layers; c.hd = p->head_dim; c.V = p->vocab_size;
+        c.I_l = p->intermediate_size / tp; c.nh_l = p->num_heads / tp; c.nkv_l = p->num_kv_heads / tp; c.V_l = p->vocab_size / tp;
+        c.qd_l = c.nh_l * c.hd; c.kvd_l = c.nkv_l * c.hd; c.qkv_l = c.qd_l + 2 * c.kvd_l;
+        c.layers.resize(c.L);
+        int layer;
+        const Kind k = parse_name(hf_name, &layer);
+        B2L_CHECK(k != K_BAD, std::string("unknown tensor name: ") + hf_name);
+        const Placement pl = place_tensor(&c, k, layer, shape, ndim);
+        win[0] = pl.row0; win[1] = pl.nrows; win[2] = pl.col0; win[3] = pl.ncols;
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return 1;
+    }
+}
+
 int b2l_finalize(b2l_ctx* c) {
     return guarded(c, [&] {
         B2L_CHECK(c->have_embed, "missing model.embed_tokens.weight");

@@ -69,6 +69,11 @@ int b2l_upload_tensor(b2l_ctx* c, const char* hf_name, const void* host_bf16, co
  * host bytes needed (8B/70B timing configs). */
 int b2l_synth_tensor(b2l_ctx* c, const char* hf_name, const int64_t* shape, int ndim, uint32_t tensor_seed,
                      float scale, float offset);
+/* The tensor-parallel shard of one HF tensor that rank p->tp_rank keeps: rows [win[0], win[0]+win[1]) x
+ * cols [win[2], win[2]+win[3]) of the full tensor (1-D tensors: one row). Pure host arithmetic, no
+ * device needed -- b2l_upload_tensor / b2l_synth_tensor use exactly this window. q/k/v/gate/up and
+ * lm_head are row (output) sharded, o/down column (input) sharded, norms and embeddings replicated. */
+int b2l_shard_window(const b2l_params* p, const char* hf_name, const int64_t* shape, int ndim, int64_t win[4]);
 /* Checks every tensor arrived, builds derived layouts, captures decode graphs. */
 int b2l_finalize(b2l_ctx* c);
 void b2l_destroy(b2l_ctx* c);
