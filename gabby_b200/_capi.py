@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(PKG, "libb2l.so")
 SYMBOLS = [
     "b2l_create", "b2l_nccl_unique_id", "b2l_shard_window", "b2l_upload_tensor", "b2l_synth_tensor", "b2l_finalize", "b2l_destroy",
     "b2l_prefill", "b2l_decode", "b2l_decode_loop", "b2l_get_logits", "b2l_set_taps", "b2l_get_hidden",
-    "b2l_get_kv_page", "b2l_get_info", "b2l_set_decode_mode", "b2l_debug_mega_profile", "b2l_last_error", "b2l_op_gemv", "b2l_op_argmax",
+    "b2l_get_kv_page", "b2l_get_info", "b2l_set_decode_mode", "b2l_debug_mega_profile", "b2l_last_error", "b2l_op_gemv", "b2l_op_argmax", "b2l_op_gemm_bf16",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
     L.b2l_op_gemv.argtypes = [C.c_int, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               C.POINTER(C.c_float)]
     L.b2l_op_argmax.argtypes = [C.c_int, vp, C.c_int, C.c_int, vp]
+    L.b2l_op_gemm_bf16.argtypes = [C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -251,3 +252,18 @@ def op_argmax(x, device=0):
     if L.b2l_op_argmax(device, _p(x), x.shape[0], x.shape[1], _p(out)) != 0:
         raise B2lError("op_argmax: " + L.b2l_last_error(None).decode())
     return out
+
+
+def op_gemm_bf16(A_bits, W_bits, epilogue=0, c_in=None, iters=0, device=0):
+    """C = A[M][K] @ W[N][K]^T on the tcgen05 tensor cores. Returns (C fp32, ms per launch or 0)."""
+    L = lib()
+    A = np.ascontiguousarray(A_bits)
+    W = np.ascontiguousarray(W_bits)
+    M, K = A.shape
+    N = W.shape[0]
+    cols = N // 2 if epilogue == 3 else N
+    Cm = np.zeros((M, cols), np.float32) if c_in is None else np.ascontiguousarray(c_in, dtype=np.float32).copy()
+    ms = C.c_float(0)
+    if L.b2l_op_gemm_bf16(device, _p(A), _p(W), _p(Cm), M, N, K, epilogue, iters, C.byref(ms)) != 0:
+        raise B2lError("op_gemm_bf16: " + L.b2l_last_error(None).decode())
+    return Cm, ms.value

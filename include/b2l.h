@@ -147,6 +147,12 @@ const char* b2l_last_error(const b2l_ctx* c);
 int b2l_op_gemv(int device, const void* W_bf16, const float* x, float* y, const void* norm_w_bf16, float eps,
                 int B, int N, int K, int mode, int iters, float* device_ms);
 int b2l_op_argmax(int device, const float* x, int B, int N, int32_t* out);
+/* Prefill GEMM on the tensor cores (tcgen05 + TMEM accumulators, TMA-fed): C = A[M][K] * W[N][K]^T, bf16 inputs,
+ * fp32 accumulate. epilogue 0: fp32 store, 1: bf16 store, 2: C += (fp32 residual), 3: SwiGLU over column pairs
+ * (W rows 2i = gate_i, 2i+1 = up_i; C is [M][N/2], bf16-rounded). C is fp32 [M][N or N/2] on the host both ways.
+ * K % 64 == 0, N % 128 == 0. iters > 0 also times `iters` launches (device_ms = average). */
+int b2l_op_gemm_bf16(int device, const void* A_bf16, const void* W_bf16, float* C, int M, int N, int K, int epilogue, int iters,
+                     float* device_ms);
 
 #ifdef __cplusplus
 }
