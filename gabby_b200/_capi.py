@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(PKG, "libb2l.so")
 SYMBOLS = [
     "b2l_create", "b2l_nccl_unique_id", "b2l_shard_window", "b2l_upload_tensor", "b2l_synth_tensor", "b2l_finalize", "b2l_destroy",
     "b2l_prefill", "b2l_decode", "b2l_decode_loop", "b2l_get_logits", "b2l_set_taps", "b2l_get_hidden",
-    "b2l_get_kv_page", "b2l_get_info", "b2l_set_decode_mode", "b2l_debug_mega_profile", "b2l_last_error", "b2l_op_gemv", "b2l_op_argmax", "b2l_op_gemm_bf16",
+    "b2l_get_kv_page", "b2l_get_info", "b2l_set_decode_mode", "b2l_set_prefill_mode", "b2l_debug_mega_profile", "b2l_last_error", "b2l_op_gemv", "b2l_op_argmax", "b2l_op_gemm_bf16",
 ]
 
 
@@ -72,6 +72,7 @@ def lib():
     L.b2l_get_kv_page.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.b2l_get_info.argtypes = [vp, C.POINTER(B2lInfo)]
     L.b2l_set_decode_mode.argtypes = [vp, C.c_int]
+    L.b2l_set_prefill_mode.argtypes = [vp, C.c_int]
     L.b2l_debug_mega_profile.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_int), vp]
     L.b2l_last_error.argtypes = [vp]
     L.b2l_last_error.restype = C.c_char_p
@@ -194,6 +195,9 @@ class Engine:
         types = np.zeros(n.value, dtype=np.int32)
         self._ck(self.L.b2l_debug_mega_profile(self.h, int(enable), _p(ns), C.byref(n), _p(types)), "mega_profile")
         return ns, types
+
+    def set_prefill_mode(self, mode: int):
+        self._ck(self.L.b2l_set_prefill_mode(self.h, mode), "set_prefill_mode")
 
     def set_decode_mode(self, mode: int):
         self._ck(self.L.b2l_set_decode_mode(self.h, mode), "set_decode_mode")

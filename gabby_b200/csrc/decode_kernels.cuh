@@ -452,6 +452,48 @@ __global__ void tp_merge_kernel(const float* __restrict__ gathered, int32_t* __r
     ids[r] = argmax_key_index(best);
 }
 
+// prefill: RMSNorm of fp32 rows -> bf16 rows (the A operand of the tensor-core GEMMs)
+__global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const uint16_t* __restrict__ w, uint16_t* __restrict__ y, int H, float eps) {
+    __shared__ float s_red[32];
+    const int r = blockIdx.x;
+    const float* xr = x + static_cast<size_t>(r) * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); i++) tot += s_red[i];
+    const float inv = rsqrtf(tot / static_cast<float>(H) + eps);
+    for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+        const uint2 nw = *reinterpret_cast<const uint2*>(w + i);
+        uint2 o;
+        o.x = pack_bf16x2(bf16lo(nw.x) * (v.x * inv), bf16hi(nw.x) * (v.y * inv));
+        o.y = pack_bf16x2(bf16lo(nw.y) * (v.z * inv), bf16hi(nw.y) * (v.w * inv));
+        *reinterpret_cast<uint2*>(y + static_cast<size_t>(r) * H + i) = o;
+    }
+}
+
+// prefill: fp32 -> bf16 (attention output -> A operand of the O projection)
+__global__ void cast_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, size_t n) {
+    const size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(x + i);
+        *reinterpret_cast<uint2*>(y + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    }
+}
+
+// prefill: gather rows (the last token of each sequence) for the lm_head
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows, float* __restrict__ dst, int H) {
+    const float* s = src + static_cast<size_t>(rows[blockIdx.x]) * H;
+    float* d = dst + static_cast<size_t>(blockIdx.x) * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) d[i] = s[i];
+}
+
 // standalone RMSNorm (parity tap of the final norm only; the hot path fuses it into the GEMV)
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const uint16_t* __restrict__ w, float* __restrict__ y,
                                int H, float eps) {

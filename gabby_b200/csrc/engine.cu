@@ -311,6 +311,96 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
     }
 }
 
+void gemm_bf16(b2l_ctx* c, const uint16_t* A, const uint16_t* W, GemmArgs g);  // defined with the tensor-map helpers below
+
+constexpr int kPfAttnChunk = 128;  // rows per split-K attention launch in the GEMM prefill path
+
+void prefill_alloc(b2l_ctx* c) {
+    if (c->pf_h) return;
+    const size_t T = static_cast<size_t>(c->p.max_prefill_tokens), H = c->H;
+    c->pf_rows = static_cast<int>(T);
+    c->pf_tokens = dalloc<int32_t>(c, T); c->pf_positions = dalloc<int32_t>(c, T); c->pf_slots = dalloc<int32_t>(c, T);
+    c->pf_last = dalloc<int32_t>(c, c->p.max_batch);
+    c->pf_h = dalloc<float>(c, T * H);
+    c->pf_qkv = dalloc<float>(c, T * c->qkv_l);
+    c->pf_attn = dalloc<float>(c, T * c->qd_l);
+    c->pf_xn = dalloc<uint16_t>(c, T * H);
+    c->pf_attn16 = dalloc<uint16_t>(c, T * c->qd_l);
+    c->pf_act16 = dalloc<uint16_t>(c, T * c->I_l);
+    if (c->p.tp_size > 1) c->pf_proj = dalloc<float>(c, T * H);
+    const size_t rows = kPfAttnChunk;
+    c->pf_part_acc = dalloc<float>(c, rows * c->nkv_l * c->nsplit * c->group * c->hd);
+    c->pf_part_ml = dalloc<float>(c, rows * c->nkv_l * c->nsplit * c->group * 2);
+    c->pf_counters = dalloc<int>(c, rows * c->nkv_l);
+    B2L_CUDA(cudaMemset(c->pf_counters, 0, sizeof(int) * rows * c->nkv_l));
+}
+
+// Prefill on the tensor cores: every new token of every sequence is one GEMM row (bf16 activations, fp32
+// accumulate and residual stream). RoPE + K/V append run for all rows first, so the split-K attention of a
+// row sees every earlier position of its sequence, including the ones appended in this same call.
+void prefill_gemm(b2l_ctx* c, int T, int n_seq, int tap_row0) {
+    prefill_alloc(c);
+    const RowMeta rm{c->pf_positions, c->pf_slots, c->d_block_tables, c->max_blocks_cap};
+    const float scale = 1.0f / sqrtf(static_cast<float>(c->hd));
+    const float eps = c->p.rms_norm_eps;
+    auto tap = [&](int slab) {
+        if (tap_row0 < 0) return;
+        float* dst = c->tap + (static_cast<size_t>(slab) * c->tap_rows_cap + tap_row0) * c->H;
+        B2L_CUDA(cudaMemcpyAsync(dst, c->pf_h, sizeof(float) * T * c->H, cudaMemcpyDeviceToDevice, c->stream));
+    };
+    launch(c, embed_kernel, dim3(T), dim3(256), 0, c->embed, c->pf_tokens, c->pf_h, c->H, c->V);
+    tap(0);
+    for (int l = 0; l < c->L; l++) {
+        const LayerWeights& w = c->layers[l];
+        const KvLayout kv{w.kv_pool, c->p.page_size, c->kvd_l};
+        rmsnorm_bf16_kernel<<<T, 256, 0, c->stream>>>(c->pf_h, w.in_norm, c->pf_xn, c->H, eps);
+        c->launched++;
+        gemm_bf16(c, c->pf_xn, w.w_qkv, GemmArgs{c->pf_qkv, nullptr, T, c->qkv_l, c->H, c->qkv_l, GEMM_STORE_F32});
+        launch(c, rope_kv_kernel, dim3(T), dim3(256), 0, c->pf_qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
+        for (int r0 = 0; r0 < T; r0 += kPfAttnChunk) {
+            const int R = std::min(kPfAttnChunk, T - r0);
+            const RowMeta rmc{c->pf_positions + r0, c->pf_slots + r0, c->d_block_tables, c->max_blocks_cap};
+            const AttnArgs aa{c->pf_qkv + static_cast<size_t>(r0) * c->qkv_l, c->qkv_l, kv, rmc, c->pf_part_acc, c->pf_part_ml, c->pf_counters,
+                              c->pf_attn + static_cast<size_t>(r0) * c->qd_l, c->qd_l, scale};
+            attn_launch(c, aa, R);
+        }
+        {
+            const size_t n = static_cast<size_t>(T) * c->qd_l;
+            cast_bf16_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, c->stream>>>(c->pf_attn, c->pf_attn16, n);
+            c->launched++;
+        }
+        if (c->p.tp_size == 1) {
+            gemm_bf16(c, c->pf_attn16, w.w_o, GemmArgs{c->pf_h, nullptr, T, c->H, c->qd_l, c->H, GEMM_ADD_F32});
+        } else {
+            gemm_bf16(c, c->pf_attn16, w.w_o, GemmArgs{c->pf_proj, nullptr, T, c->H, c->qd_l, c->H, GEMM_STORE_F32});
+            const size_t n = static_cast<size_t>(T) * c->H;
+            B2L_NCCL(nccl().AllReduce(c->pf_proj, c->pf_proj, n, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream));
+            launch(c, add_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, c->pf_h, static_cast<const float*>(c->pf_proj), static_cast<int>(n));
+        }
+        rmsnorm_bf16_kernel<<<T, 256, 0, c->stream>>>(c->pf_h, w.post_norm, c->pf_xn, c->H, eps);
+        c->launched++;
+        gemm_bf16(c, c->pf_xn, w.w_gu, GemmArgs{nullptr, c->pf_act16, T, 2 * c->I_l, c->H, c->I_l, GEMM_SWIGLU_BF16});
+        if (c->p.tp_size == 1) {
+            gemm_bf16(c, c->pf_act16, w.w_down, GemmArgs{c->pf_h, nullptr, T, c->H, c->I_l, c->H, GEMM_ADD_F32});
+        } else {
+            gemm_bf16(c, c->pf_act16, w.w_down, GemmArgs{c->pf_proj, nullptr, T, c->H, c->I_l, c->H, GEMM_STORE_F32});
+            const size_t n = static_cast<size_t>(T) * c->H;
+            B2L_NCCL(nccl().AllReduce(c->pf_proj, c->pf_proj, n, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream));
+            launch(c, add_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, c->pf_h, static_cast<const float*>(c->pf_proj), static_cast<int>(n));
+        }
+        tap(l + 1);
+    }
+    if (tap_row0 >= 0) {
+        float* dst = c->tap + (static_cast<size_t>(c->L + 1) * c->tap_rows_cap + tap_row0) * c->H;
+        rmsnorm_kernel<<<T, 256, 0, c->stream>>>(c->pf_h, c->final_norm, dst, c->H, eps);
+        c->launched++;
+    }
+    // lm_head only for the last token of each sequence: gather those rows, then the (fused final norm) GEMV
+    gather_rows_kernel<<<n_seq, 256, 0, c->stream>>>(c->pf_h, c->pf_last, c->h, c->H);
+    c->launched++;
+    gemv(c, c->lm_head, c->h, c->H, c->seq_logits, c->V_l, c->final_norm, c->V_l, c->H, 0, n_seq);
+}
+
 Graph& decode_graph(b2l_ctx* c, int R, bool with_advance) {
     const int key = R + (with_advance ? 1000 : 0);
     auto it = c->decode_graphs.find(key);
@@ -845,6 +935,7 @@ int b2l_finalize(b2l_ctx* c) {
             B2L_CHECK(c->layers[l].have == all, "layer " + std::to_string(l) + " is missing tensors");
         B2L_CUDA(cudaDeviceSynchronize());
         ensure_out_ids(c, 256);
+        c->pf_ok = c->qkv_l % 128 == 0 && c->H % 128 == 0 && (2 * c->I_l) % 128 == 0 && c->H % 64 == 0 && c->qd_l % 64 == 0 && c->I_l % 64 == 0;
         mega_setup(c);
         c->decode_mode = c->mega_ok ? 1 : 0;
         c->finalized = true;
@@ -950,10 +1041,30 @@ int b2l_prefill(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* q_l
         for (int64_t i = 0; i < total; i++) B2L_CHECK(tokens[i] >= 0 && tokens[i] < c->V, "token id out of range");
         if (c->taps) B2L_CHECK(total <= c->tap_rows_cap, "taps: prefill larger than the tap buffer");
         upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
-        // Round-1 prefill: chunks of <= 8 consecutive positions through the decode kernels
+        const bool use_gemm = c->pf_ok && (c->prefill_mode == 1 || (c->prefill_mode < 0 && total >= 64));
+        if (use_gemm) {
+            prefill_alloc(c);
+            std::vector<int32_t> pos(total), slot(total), last(n_seq);
+            int64_t t0 = 0;
+            for (int i = 0; i < n_seq; i++) {
+                for (int j = 0; j < q_lens[i]; j++) {
+                    pos[t0 + j] = ctx_lens[i] + j;
+                    slot[t0 + j] = i;
+                }
+                t0 += q_lens[i];
+                last[i] = static_cast<int32_t>(t0 - 1);
+            }
+            B2L_CUDA(cudaMemcpyAsync(c->pf_tokens, tokens, sizeof(int32_t) * total, cudaMemcpyHostToDevice, c->stream));
+            B2L_CUDA(cudaMemcpyAsync(c->pf_positions, pos.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, c->stream));
+            B2L_CUDA(cudaMemcpyAsync(c->pf_slots, slot.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, c->stream));
+            B2L_CUDA(cudaMemcpyAsync(c->pf_last, last.data(), sizeof(int32_t) * n_seq, cudaMemcpyHostToDevice, c->stream));
+            B2L_CUDA(cudaStreamSynchronize(c->stream));   // pos/slot/last are stack vectors
+            prefill_gemm(c, static_cast<int>(total), n_seq, c->taps ? 0 : -1);
+        }
+        // exact-activation prefill: chunks of <= 8 consecutive positions through the decode kernels
         // (each chunk appends its K/V before its attention runs, so causality holds inside it).
         int64_t tok0 = 0;
-        for (int i = 0; i < n_seq; i++) {
+        for (int i = 0; i < n_seq && !use_gemm; i++) {
             for (int c0 = 0; c0 < q_lens[i]; c0 += 8) {
                 const int R = std::min(8, q_lens[i] - c0);
                 int32_t pos[8], slot[8];
@@ -1081,6 +1192,15 @@ int b2l_debug_mega_profile(b2l_ctx* c, int enable, uint64_t* out_ns, int* n_phas
             for (int i = 0; i < c->mega_n_phases; i++) phase_types[i] = ph[i].type;
         }
         if (!enable) c->mega_prof = nullptr;
+    });
+}
+
+int b2l_set_prefill_mode(b2l_ctx* c, int mode) {
+    return guarded(c, [&] {
+        B2L_CHECK(mode >= -1 && mode <= 1, "prefill mode must be -1 (auto), 0 (chunked decode kernels) or 1 (tcgen05 GEMMs)");
+        require_ready(c);
+        B2L_CHECK(mode != 1 || c->pf_ok, "tcgen05 prefill unavailable: projection widths must be multiples of 128 (N) and 64 (K)");
+        c->prefill_mode = mode;
     });
 }
 

@@ -104,6 +104,15 @@ struct b2l_ctx {
     int* mega_abort = nullptr;               // pinned host flag, device-visible
     unsigned long long* mega_prof = nullptr; // device [4][n_phases+1] phase timestamps (debug)
 
+    // tensor-core prefill (gemm_tcgen05.cuh): bf16 activations, sized for max_prefill_tokens rows
+    int prefill_mode = -1;           // -1 auto (GEMM path for >= 64 new tokens), 0 chunked decode kernels, 1 GEMM path
+    bool pf_ok = false;              // shapes satisfy the GEMM constraints
+    int pf_rows = 0;
+    int32_t *pf_tokens = nullptr, *pf_positions = nullptr, *pf_slots = nullptr, *pf_last = nullptr;
+    float *pf_h = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_proj = nullptr, *pf_part_acc = nullptr, *pf_part_ml = nullptr;
+    uint16_t *pf_xn = nullptr, *pf_attn16 = nullptr, *pf_act16 = nullptr;
+    int* pf_counters = nullptr;
+
     // tensor parallelism (NCCL, loaded with dlopen only when tp_size > 1)
     void* nccl_comm = nullptr;
     float* tp_pack = nullptr;        // [max_rows][2]   (value, index) of this rank's argmax

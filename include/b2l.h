@@ -128,6 +128,11 @@ int b2l_get_info(b2l_ctx* c, b2l_info* out);
 /* decode implementation: 0 multi-kernel CUDA graph, 1 persistent megakernel (batch 1) */
 int b2l_set_decode_mode(b2l_ctx* c, int mode);
 
+/* prefill implementation: 1 = tcgen05/TMEM GEMMs over all new tokens (bf16 activations, fp32 accumulate and
+ * residual stream), 0 = 8-token chunks through the decode kernels (fp32 activations), -1 = auto (GEMMs for
+ * >= 64 new tokens). */
+int b2l_set_prefill_mode(b2l_ctx* c, int mode);
+
 /* Debug: per-phase device timestamps (globaltimer ns) of the last token of the last megakernel
  * launch. enable=1 arms it; out_ns (optional) is [9][n_phases+1], column = phase: rows 0-3 CTA 0
  * {phase entry, dependency barrier passed, input vector loaded, phase end}, rows 4-7 the same for

@@ -203,6 +203,7 @@ orc_seq* orc_seq_create(const orc_model* m, int flags) {
 }
 
 void orc_seq_reset(orc_seq* s) { s->len = 0; }
+void orc_seq_set_flags(orc_seq* s, int flags) { s->flags = flags; }
 int orc_seq_len(const orc_seq* s) { return s->len; }
 void orc_seq_destroy(orc_seq* s) { delete s; }
 

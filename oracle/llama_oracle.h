@@ -67,6 +67,9 @@ void orc_model_destroy(orc_model* m);
 
 orc_seq* orc_seq_create(const orc_model* m, int flags);
 void orc_seq_reset(orc_seq* s);
+/* change the rounding-point flags for subsequent forwards (prefill on the tensor-core path rounds linear inputs
+ * to bf16, decode does not) */
+void orc_seq_set_flags(orc_seq* s, int flags);
 int orc_seq_len(const orc_seq* s);
 void orc_seq_destroy(orc_seq* s);
 

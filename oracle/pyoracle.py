@@ -52,6 +52,7 @@ def _bind(lib):
     lib.orc_seq_create.restype = vp
     lib.orc_seq_create.argtypes = [vp, C.c_int]
     lib.orc_seq_reset.argtypes = [vp]
+    lib.orc_seq_set_flags.argtypes = [vp, C.c_int]
     lib.orc_seq_len.argtypes = [vp]
     lib.orc_seq_destroy.argtypes = [vp]
     lib.orc_seq_forward.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
@@ -179,6 +180,9 @@ class OracleSeq:
 
     def reset(self):
         self.L.orc_seq_reset(self.h)
+
+    def set_flags(self, flags: int):
+        self.L.orc_seq_set_flags(self.h, flags)
 
     def forward(self, tokens, logits_all: bool = False, want_hidden: bool = False):
         """-> (logits [rows, V] fp32, hidden [(L+2), n, H] fp32 or None)"""

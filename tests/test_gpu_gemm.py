@@ -52,3 +52,62 @@ def test_gemm_rejects_bad_shapes():
         _capi.op_gemm_bf16(A, W)
     with pytest.raises(_capi.B2lError, match="multiple of 128"):
         _capi.op_gemm_bf16(np.zeros((128, 64), np.uint16), np.zeros((96, 64), np.uint16))
+
+
+# ---------------------------------------------------------------------------------------------
+# the GEMM prefill path inside the engine against the oracle with the same rounding points
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("preset,layers,seed,lens", [
+    ("tiny", None, 1234, [70]),
+    ("tiny128", None, 77, [33, 90, 5]),          # ragged batch, one sequence shorter than a GEMM tile
+    ("1b", 2, 5, [130]),                          # full 1B width
+])
+def test_gemm_prefill_matches_oracle_with_bf16_activations(preset, layers, seed, lens):
+    from oracle import pyoracle as po
+    from tests.helpers import synth_tensors, make_engine, contiguous_tables, cosine
+    arch, tensors = synth_tensors(preset, layers, seed)
+    prompts = [synth.synth_prompt(n, arch.vocab_size, arch.bos_token_id, 300 + i) for i, n in enumerate(lens)]
+    eng = make_engine(arch, tensors, max_batch=len(lens), max_positions=256, max_prefill_tokens=256)
+    eng.set_prefill_mode(1)
+    eng.set_taps(True)
+    bt = contiguous_tables(len(lens), eng.max_blocks)
+    first = eng.prefill(prompts, [0] * len(lens), bt)
+    logits = eng.logits(0, len(lens))
+    hidden_last = eng.hidden(arch.num_hidden_layers, 0, sum(lens))
+    eng.set_taps(False)
+    ids, _ = eng.decode_loop(first, lens, bt, 8)
+    om = po.OracleModel(arch, tensors, 256)
+    row = 0
+    for i, p in enumerate(prompts):
+        s = om.seq(po.ORC_KV_BF16 | po.ORC_ACT_BF16)
+        ol, oh = s.forward(p, want_hidden=True)
+        # bf16 activations on both sides, but the GPU rounds the lm_head input only on the oracle side and sums in a
+        # different order: tolerance 3e-2 on logits of scale 2-6, cosine 0.9999
+        assert np.abs(logits[i] - ol[0]).max() < 3e-2 and cosine(logits[i], ol[0]) > 0.9999, i
+        assert np.abs(hidden_last[row:row + len(p)] - oh[arch.num_hidden_layers]).max() < 3e-2
+        row += len(p)
+        s.set_flags(po.ORC_KV_BF16)                       # decode keeps fp32 activations
+        tok, want = int(np.argmax(ol[0])), []
+        for _ in range(9):
+            want.append(tok)
+            lg, _ = s.forward([tok])
+            tok = int(np.argmax(lg[0]))
+        got = [int(first[i])] + ids[:, i].tolist()
+        assert got == want, (i, got, want)
+
+
+def test_gemm_prefill_continues_cached_context_like_the_exact_path():
+    from tests.helpers import synth_tensors, make_engine, contiguous_tables
+    arch, tensors = synth_tensors("tiny", None, 1234)
+    prompt = synth.synth_prompt(150, arch.vocab_size, arch.bos_token_id, 9)
+    outs = []
+    for mode in (0, 1):
+        eng = make_engine(arch, tensors, max_positions=256, max_prefill_tokens=256)
+        eng.set_prefill_mode(mode)
+        bt = contiguous_tables(1, eng.max_blocks)
+        eng.prefill([prompt[:70]], [0], bt)
+        nxt = eng.prefill([prompt[70:]], [70], bt)      # second call appends to the cached 70 tokens
+        outs.append((int(nxt[0]), eng.logits(0, 1)[0].copy()))
+    assert outs[0][0] == outs[1][0]
+    assert np.abs(outs[0][1] - outs[1][1]).max() < 5e-2
