@@ -16,6 +16,7 @@
 #include "decode_kernels.cuh"
 #include "mega_decode.cuh"
 #include "gemm_tcgen05.cuh"
+#include "flash_prefill.cuh"
 #include "synth.cuh"
 
 using namespace b2l;
@@ -332,6 +333,7 @@ void prefill_alloc(b2l_ctx* c) {
     c->pf_part_acc = dalloc<float>(c, rows * c->nkv_l * c->nsplit * c->group * c->hd);
     c->pf_part_ml = dalloc<float>(c, rows * c->nkv_l * c->nsplit * c->group * 2);
     c->pf_counters = dalloc<int>(c, rows * c->nkv_l);
+    c->pf_tiles = dalloc<PrefillTile>(c, T / 1 + static_cast<size_t>(c->p.max_batch));  // <= one tile per row in the worst case
     B2L_CUDA(cudaMemset(c->pf_counters, 0, sizeof(int) * rows * c->nkv_l));
 }
 
@@ -357,14 +359,31 @@ void prefill_gemm(b2l_ctx* c, int T, int n_seq, int tap_row0) {
         c->launched++;
         gemm_bf16(c, c->pf_xn, w.w_qkv, GemmArgs{c->pf_qkv, nullptr, T, c->qkv_l, c->H, c->qkv_l, GEMM_STORE_F32});
         launch(c, rope_kv_kernel, dim3(T), dim3(256), 0, c->pf_qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
-        for (int r0 = 0; r0 < T; r0 += kPfAttnChunk) {
-            const int R = std::min(kPfAttnChunk, T - r0);
-            const RowMeta rmc{c->pf_positions + r0, c->pf_slots + r0, c->d_block_tables, c->max_blocks_cap};
-            const AttnArgs aa{c->pf_qkv + static_cast<size_t>(r0) * c->qkv_l, c->qkv_l, kv, rmc, c->pf_part_acc, c->pf_part_ml, c->pf_counters,
-                              c->pf_attn + static_cast<size_t>(r0) * c->qd_l, c->qd_l, scale};
-            attn_launch(c, aa, R);
-        }
-        {
+        if (c->hd == 64 || c->hd == 128) {
+            // flash-style causal attention over the paged cache, tensor-core S and PV, bf16 output
+            FlashArgs fa{c->pf_qkv, c->qkv_l, kv, c->d_block_tables, c->max_blocks_cap, static_cast<const PrefillTile*>(c->pf_tiles),
+                         c->pf_attn16, c->qd_l, c->group, scale * 1.4426950408889634f};
+            const dim3 grid(c->pf_n_tiles, c->nh_l);
+            if (c->hd == 64) {
+                flash_prefill_kernel<64><<<grid, kFlashThreads, 3 * 64 * (64 + 8) * 2, c->stream>>>(fa);
+            } else {
+                static bool configured = false;
+                if (!configured) {
+                    B2L_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * (128 + 8) * 2));
+                    configured = true;
+                }
+                flash_prefill_kernel<128><<<grid, kFlashThreads, 3 * 64 * (128 + 8) * 2, c->stream>>>(fa);
+            }
+            B2L_CUDA(cudaGetLastError());
+            c->launched++;
+        } else {
+            for (int r0 = 0; r0 < T; r0 += kPfAttnChunk) {
+                const int R = std::min(kPfAttnChunk, T - r0);
+                const RowMeta rmc{c->pf_positions + r0, c->pf_slots + r0, c->d_block_tables, c->max_blocks_cap};
+                const AttnArgs aa{c->pf_qkv + static_cast<size_t>(r0) * c->qkv_l, c->qkv_l, kv, rmc, c->pf_part_acc, c->pf_part_ml, c->pf_counters,
+                                  c->pf_attn + static_cast<size_t>(r0) * c->qd_l, c->qd_l, scale};
+                attn_launch(c, aa, R);
+            }
             const size_t n = static_cast<size_t>(T) * c->qd_l;
             cast_bf16_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, c->stream>>>(c->pf_attn, c->pf_attn16, n);
             c->launched++;
@@ -1058,6 +1077,15 @@ int b2l_prefill(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* q_l
             B2L_CUDA(cudaMemcpyAsync(c->pf_positions, pos.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, c->stream));
             B2L_CUDA(cudaMemcpyAsync(c->pf_slots, slot.data(), sizeof(int32_t) * total, cudaMemcpyHostToDevice, c->stream));
             B2L_CUDA(cudaMemcpyAsync(c->pf_last, last.data(), sizeof(int32_t) * n_seq, cudaMemcpyHostToDevice, c->stream));
+            std::vector<PrefillTile> tiles;   // 64 consecutive positions of one sequence per attention CTA
+            int64_t row = 0;
+            for (int i = 0; i < n_seq; i++) {
+                for (int j = 0; j < q_lens[i]; j += kFlashBM)
+                    tiles.push_back(PrefillTile{static_cast<int>(row + j), std::min(kFlashBM, q_lens[i] - j), ctx_lens[i] + j, i});
+                row += q_lens[i];
+            }
+            c->pf_n_tiles = static_cast<int>(tiles.size());
+            B2L_CUDA(cudaMemcpyAsync(c->pf_tiles, tiles.data(), sizeof(PrefillTile) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
             B2L_CUDA(cudaStreamSynchronize(c->stream));   // pos/slot/last are stack vectors
             prefill_gemm(c, static_cast<int>(total), n_seq, c->taps ? 0 : -1);
         }

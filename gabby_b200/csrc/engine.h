@@ -112,6 +112,8 @@ struct b2l_ctx {
     float *pf_h = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_proj = nullptr, *pf_part_acc = nullptr, *pf_part_ml = nullptr;
     uint16_t *pf_xn = nullptr, *pf_attn16 = nullptr, *pf_act16 = nullptr;
     int* pf_counters = nullptr;
+    void* pf_tiles = nullptr;        // device PrefillTile[] (flash prefill attention work list)
+    int pf_n_tiles = 0;
 
     // tensor parallelism (NCCL, loaded with dlopen only when tp_size > 1)
     void* nccl_comm = nullptr;

@@ -80,12 +80,13 @@ def test_gemm_prefill_matches_oracle_with_bf16_activations(preset, layers, seed,
     om = po.OracleModel(arch, tensors, 256)
     row = 0
     for i, p in enumerate(prompts):
-        s = om.seq(po.ORC_KV_BF16 | po.ORC_ACT_BF16)
+        s = om.seq(po.ORC_KV_BF16 | po.ORC_ACT_BF16 | po.ORC_QP_BF16)   # bf16 linear inputs, bf16 q and softmax probabilities
         ol, oh = s.forward(p, want_hidden=True)
         # bf16 activations on both sides, but the GPU rounds the lm_head input only on the oracle side and sums in a
         # different order: tolerance 6e-2 on logits of scale 2-6 (observed 3e-2), cosine 0.9999
         assert np.abs(logits[i] - ol[0]).max() < 6e-2 and cosine(logits[i], ol[0]) > 0.9999, i
-        assert np.abs(hidden_last[row:row + len(p)] - oh[arch.num_hidden_layers]).max() < 3e-2
+        hd = np.abs(hidden_last[row:row + len(p)] - oh[arch.num_hidden_layers])
+        assert hd.max() < 8e-2 and hd.mean() < 4e-3 and cosine(hidden_last[row:row + len(p)], oh[arch.num_hidden_layers]) > 0.9999, (i, float(hd.max()))
         row += len(p)
         s.set_flags(po.ORC_KV_BF16)                       # decode keeps fp32 activations
         tok, want = int(np.argmax(ol[0])), []
