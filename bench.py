@@ -244,6 +244,78 @@ def run_8b_tp(args):
         dist.destroy_process_group()
 
 
+def run_3b_b8(args):
+    """BASELINE configs[2]: Llama-3.2-3B bf16, batch 8, 2048-token prefill (tcgen05 GEMMs + flash attention) and
+    `steps` greedy decode steps of the whole batch (multi-kernel path). One GPU. `value` = decode tok/s of the
+    batch; the prefill throughput and its tensor-roofline fraction ride along in `prefill`."""
+    import torch
+    from gabby_b200 import _capi, _host, synth
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    K, W, B, S = args.steps, max(3, args.warmup), 8, 2048
+    arch = synth.preset("3b")
+    max_positions = S + 2 * (K + W) + 64
+    eng = _capi.Engine(arch, _host.rope_table(arch, max_positions), max_batch=B, max_positions=max_positions, page_size=PAGE,
+                       max_prefill_tokens=B * S, device=local)
+    for name, shape, scale, off in synth.tensor_specs(arch):
+        eng.synth(name, shape, synth.tensor_seed(name, SEED), scale, off)
+    eng.finalize()
+    info = eng.info()
+    bt = np.arange(B * eng.max_blocks, dtype=np.int32).reshape(B, eng.max_blocks)
+    prompts = [synth.synth_prompt(S, arch.vocab_size, arch.bos_token_id, SEED + 10 + i) for i in range(B)]
+    eng.prefill(prompts, [0] * B, bt)                      # warm-up (allocations, tensor maps)
+    torch.cuda.synchronize()
+    pf = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        first = eng.prefill(prompts, [0] * B, bt)         # host tokens in, first ids out: end to end
+        pf.append(time.perf_counter() - t0)
+    pf_s = min(pf)
+    lin = sum(int(np.prod(s)) for n, s, _, _ in synth.tensor_specs(arch) if "proj" in n)
+    flops = 2.0 * B * S * lin + 2.0 * 2.0 * (S * S / 2.0) * arch.num_attention_heads * arch.head_dim * arch.num_hidden_layers * B
+    try:
+        tf_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"]
+    except Exception:
+        tf_peak = 1400.0
+    pos = [S] * B
+    eng.decode_loop(first, pos, bt, W)
+    l0 = eng.info().kernels_launched
+    with ClockSampler(local) as clk:
+        ids, dev_ms = eng.decode_loop(first, pos, bt, K)
+        reps, extra = 0, 0.0
+        while dev_ms + extra < 1500.0 and reps < 16:
+            _, m = eng.decode_loop(first, pos, bt, K)
+            extra += m; reps += 1
+    launches = (eng.info().kernels_launched - l0) // (1 + reps)
+    ms_per_step = dev_ms / K
+    cur, p = first.copy(), list(pos)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        cur = eng.decode(cur, p, bt); p = [x + 1 for x in p]
+    e2e = B * K / (time.perf_counter() - t0)
+    kv_per_tok = 2 * arch.num_hidden_layers * arch.num_key_value_heads * arch.head_dim * 2
+    bytes_per_step = info.stream_bytes_per_token + B * ((S + K / 2.0) * kv_per_tok + kv_per_tok)
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per_step / (ms_per_step * 1e-3) / 1e9
+    line = {
+        "metric": "decode_tokens_per_s", "value": B * 1000.0 / ms_per_step, "unit": "tok/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "llama-3.2-3b bf16 batch 8: 2048-token prefill + greedy decode (BASELINE configs[2])", "batch": B,
+                   "context": [S, S + K], "kv": f"paged bf16, page {PAGE}", "l2": "inputs larger than L2", "decode_mode": 0},
+        "prefill": {"tokens": B * S, "seconds": pf_s, "tok_per_s": B * S / pf_s, "algorithmic_tflop": flops / 1e12,
+                    "achieved_tflops": flops / pf_s / 1e12, "peak_tflops": tf_peak, "frac": flops / pf_s / 1e12 / tf_peak,
+                    "note": "tcgen05 GEMMs + flash attention; wall clock incl. H2D of tokens and D2H of the first ids"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "bytes_per_step": bytes_per_step,
+                     "kernel": f"batch-8 decode step = CUDA graph of {launches // K} kernels"},
+        "cpu_baseline": None,
+        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": B * (12 + 4 * eng.max_blocks), "d2h_bytes_per_step": 4 * B},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,7 +324,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-mode", type=int, default=None)
-    ap.add_argument("--workload", default="1b-decode", choices=["1b-decode", "8b-tp"],
+    ap.add_argument("--workload", default="1b-decode", choices=["1b-decode", "8b-tp", "3b-b8"],
                     help="1b-decode: BASELINE configs[1], N replicas (default). 8b-tp: configs[3], Llama-3.1-8B tensor-parallel over N GPUs")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--context", type=int, default=4096)
@@ -262,6 +334,8 @@ def main():
 
     if args.workload == "8b-tp":
         return run_8b_tp(args)
+    if args.workload == "3b-b8":
+        return run_3b_b8(args)
     rank, world, local = dist_env()
     K, W = args.steps, max(3, args.warmup)
     import torch
