@@ -170,7 +170,7 @@ void launch(b2l_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t 
     c->launched++;
 }
 
-constexpr size_t kGemvSmemBudget = 96 * 1024;
+constexpr size_t kGemvSmemBudget = 32 * 1024;  // x tile per CTA: small enough for 6+ CTAs per SM at batch 8
 
 int gemv_kt(int B, int K) {
     const int cap = static_cast<int>(kGemvSmemBudget / (4 * B)) / 256 * 256;

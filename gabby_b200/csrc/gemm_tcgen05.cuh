@@ -18,7 +18,7 @@
 
 namespace b2l {
 
-constexpr int kGemmBM = 128, kGemmBK = 64, kGemmStages = 4, kGemmThreads = 192;
+constexpr int kGemmBM = 128, kGemmBK = 64, kGemmStages = 3, kGemmThreads = 192;  // 3 stages x 32 KB: two CTAs per SM, one CTA's epilogue overlaps the other's main loop
 
 enum GemmEpilogue { GEMM_STORE_F32 = 0, GEMM_STORE_BF16 = 1, GEMM_ADD_F32 = 2, GEMM_SWIGLU_BF16 = 3 };
 
@@ -76,7 +76,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
     constexpr uint32_t kStageA = kGemmBM * kGemmBK * 2, kStageB = BN * kGemmBK * 2;
     constexpr uint32_t kTmemCols = BN;  // fp32 accumulator: one column per output column (power of two >= 32)
