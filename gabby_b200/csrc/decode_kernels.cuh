@@ -272,33 +272,42 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
         for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
     }
 
-    for (int jb = j0; jb < j1; jb += NG) {
-        const int j = jb + grp;
-        const bool valid = j < j1;
-        uint4 kw = make_uint4(0, 0, 0, 0), vw = make_uint4(0, 0, 0, 0);
-        if (valid) {
-            const int page = bt[j / a.kv.page_size], off = j % a.kv.page_size;
-            kw = *reinterpret_cast<const uint4*>(a.kv.at(page, 0, off) + kvh * HD + sl * 8);
-            vw = *reinterpret_cast<const uint4*>(a.kv.at(page, 1, off) + kvh * HD + sl * 8);
+    constexpr int U = 4;  // tokens in flight per lane group: the loop is bound by load latency, not by math
+    for (int jb = j0; jb < j1; jb += NG * U) {
+        uint4 kw[U], vw[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + u * NG + grp;
+            kw[u] = make_uint4(0, 0, 0, 0);
+            vw[u] = make_uint4(0, 0, 0, 0);
+            if (j < j1) {
+                const int page = bt[j / a.kv.page_size], off = j % a.kv.page_size;
+                kw[u] = ldg_stream(reinterpret_cast<const uint4*>(a.kv.at(page, 0, off) + kvh * HD + sl * 8));
+                vw[u] = ldg_stream(reinterpret_cast<const uint4*>(a.kv.at(page, 1, off) + kvh * HD + sl * 8));
+            }
         }
-        const float kf[8] = {bf16lo(kw.x), bf16hi(kw.x), bf16lo(kw.y), bf16hi(kw.y),
-                             bf16lo(kw.z), bf16hi(kw.z), bf16lo(kw.w), bf16hi(kw.w)};
-        const float vf[8] = {bf16lo(vw.x), bf16hi(vw.x), bf16lo(vw.y), bf16hi(vw.y),
-                             bf16lo(vw.z), bf16hi(vw.z), bf16lo(vw.w), bf16hi(vw.w)};
 #pragma unroll
-        for (int g = 0; g < GROUP; g++) {
-            float s = 0.f;
+        for (int u = 0; u < U; u++) {
+            const bool valid = jb + u * NG + grp < j1;
+            const float kf[8] = {bf16lo(kw[u].x), bf16hi(kw[u].x), bf16lo(kw[u].y), bf16hi(kw[u].y),
+                                 bf16lo(kw[u].z), bf16hi(kw[u].z), bf16lo(kw[u].w), bf16hi(kw[u].w)};
+            const float vf[8] = {bf16lo(vw[u].x), bf16hi(vw[u].x), bf16lo(vw[u].y), bf16hi(vw[u].y),
+                                 bf16lo(vw[u].z), bf16hi(vw[u].z), bf16lo(vw[u].w), bf16hi(vw[u].w)};
 #pragma unroll
-            for (int i = 0; i < 8; i++) s = fmaf(q[g][i], kf[i], s);
+            for (int g = 0; g < GROUP; g++) {
+                float s = 0.f;
 #pragma unroll
-            for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (valid) {
-                const float mn = fmaxf(m[g], s);
-                const float corr = __expf(m[g] - mn), p = __expf(s - mn);
-                l[g] = l[g] * corr + p;
+                for (int i = 0; i < 8; i++) s = fmaf(q[g][i], kf[i], s);
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[g][i] = fmaf(acc[g][i], corr, p * vf[i]);
-                m[g] = mn;
+                for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (valid) {
+                    const float mn = fmaxf(m[g], s);
+                    const float corr = __expf(m[g] - mn), p = __expf(s - mn);
+                    l[g] = l[g] * corr + p;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc[g][i] = fmaf(acc[g][i], corr, p * vf[i]);
+                    m[g] = mn;
+                }
             }
         }
     }

@@ -17,6 +17,7 @@
 #include "mega_decode.cuh"
 #include "gemm_tcgen05.cuh"
 #include "flash_prefill.cuh"
+#include "skinny_gemm.cuh"
 #include "synth.cuh"
 
 using namespace b2l;
@@ -252,6 +253,51 @@ void tap_copy(b2l_ctx* c, int slab, int row0, const float* src, int R) {
     B2L_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * R * c->H, cudaMemcpyDeviceToDevice, c->stream));
 }
 
+CUtensorMap make_kmajor_map(const uint16_t* ptr, int64_t rows, int64_t cols, int box_rows);  // defined below
+
+// ---- batched decode (2..16 rows) on the tensor cores -----------------------------------------------
+constexpr size_t kSkinnySmem = static_cast<size_t>(kSkinnyStages) * (128 * kGemmBK * 2 + 4096) + 16 * kSkinnyStages + 64 + 1024;
+
+void skinny_setup(b2l_ctx* c) {
+    c->skinny_ok = false;
+    const bool shapes = c->qkv_l % 128 == 0 && c->H % 128 == 0 && (2 * c->I_l) % 128 == 0 && c->V_l % 128 == 0 &&
+                        c->H % 64 == 0 && c->qd_l % 64 == 0 && c->I_l % 64 == 0 && c->p.max_batch >= 2;
+    if (!shapes) return;
+    c->sk_xh = dalloc<uint16_t>(c, static_cast<size_t>(32) * c->H);
+    c->sk_xq = dalloc<uint16_t>(c, static_cast<size_t>(32) * c->qd_l);
+    c->sk_xi = dalloc<uint16_t>(c, static_cast<size_t>(32) * c->I_l);
+    B2L_CUDA(cudaMemset(c->sk_xh, 0, sizeof(uint16_t) * 32 * c->H));
+    B2L_CUDA(cudaMemset(c->sk_xq, 0, sizeof(uint16_t) * 32 * c->qd_l));
+    B2L_CUDA(cudaMemset(c->sk_xi, 0, sizeof(uint16_t) * 32 * c->I_l));
+    const size_t max_n = std::max<size_t>(static_cast<size_t>(c->V_l), static_cast<size_t>(2) * c->I_l);
+    c->sk_partial_floats = std::max<size_t>(max_n * 16, static_cast<size_t>(32) * 16 * 8192);
+    c->sk_partial = dalloc<float>(c, c->sk_partial_floats);
+    B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSkinnySmem)));
+    B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSkinnySmem)));
+    c->skinny_ok = true;
+}
+
+// y (op)= W x for R (2..16) activation rows: prep (hi/lo bf16 [+ RMSNorm]) -> tcgen05 skinny GEMM -> split reduce + epilogue
+void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, int ldx, const uint16_t* norm_w, uint16_t* xbuf,
+                   float* y, int ldy, int mode, int R) {
+    const int BT = R <= 8 ? 16 : 32, T = BT / 2;
+    if (norm_w) launch(c, split_bf16_kernel<true>, dim3(R), dim3(256), 0, x, ldx, norm_w, xbuf, K, T, c->p.rms_norm_eps);
+    else launch(c, split_bf16_kernel<false>, dim3(R), dim3(256), 0, x, ldx, static_cast<const uint16_t*>(nullptr), xbuf, K, T, 0.f);
+    const int n_tiles = N / 128, n_kblocks = K / kGemmBK;
+    // two CTAs per SM are resident: size the K split so the grid is (at most) one full wave
+    int ksplit = std::max(1, std::min({2 * c->prop.multiProcessorCount / n_tiles, n_kblocks / 2, 32}));
+    while (static_cast<size_t>(ksplit) * T * N > c->sk_partial_floats && ksplit > 1) ksplit--;
+    const int per_split = (n_kblocks + ksplit - 1) / ksplit;
+    ksplit = (n_kblocks + per_split - 1) / per_split;
+    const CUtensorMap mw = make_kmajor_map(W, N, K, 128), mx = make_kmajor_map(xbuf, BT, K, BT);
+    const dim3 grid(n_tiles, ksplit);
+    const size_t smem = kSkinnySmem;
+    if (BT == 16) launch(c, skinny_gemm_kernel<16>, grid, dim3(kSkinnyThreads), smem, mw, mx, c->sk_partial, N, n_kblocks, per_split);
+    else launch(c, skinny_gemm_kernel<32>, grid, dim3(kSkinnyThreads), smem, mw, mx, c->sk_partial, N, n_kblocks, per_split);
+    const int cols = mode == 2 ? N / 2 : N;
+    launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, y, ldy);
+}
+
 // h += all_reduce_sum(proj) over the TP ranks (fp32; the messages are R x H x 4 bytes: latency-bound)
 void tp_allreduce_add(b2l_ctx* c, int R) {
     const size_t n = static_cast<size_t>(R) * c->H;
@@ -281,24 +327,22 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
     for (int l = 0; l < c->L; l++) {
         const LayerWeights& w = c->layers[l];
         const KvLayout kv{w.kv_pool, c->p.page_size, c->kvd_l};
-        gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
+        const bool sk = c->skinny_ok && R >= 2 && R <= 16;   // batched decode: projections on the tensor cores
+        if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R);
+        else gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
         launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
         const AttnArgs aa{c->qkv, c->qkv_l, kv, rm, c->part_acc, c->part_ml, c->attn_counters, c->attn, c->qd_l, scale};
         attn_launch(c, aa, R);
-        if (c->p.tp_size == 1) {
-            gemv(c, w.w_o, c->attn, c->qd_l, c->h, c->H, nullptr, c->H, c->qd_l, 1, R);
-        } else {
-            // row-parallel O: every rank holds a K slice, the partial products are summed over NVLink
-            gemv(c, w.w_o, c->attn, c->qd_l, c->proj, c->H, nullptr, c->H, c->qd_l, 0, R);
-            tp_allreduce_add(c, R);
-        }
-        gemv(c, w.w_gu, c->h, c->H, c->act, c->I_l, w.post_norm, 2 * c->I_l, c->H, 2, R);
-        if (c->p.tp_size == 1) {
-            gemv(c, w.w_down, c->act, c->I_l, c->h, c->H, nullptr, c->H, c->I_l, 1, R);
-        } else {
-            gemv(c, w.w_down, c->act, c->I_l, c->proj, c->H, nullptr, c->H, c->I_l, 0, R);
-            tp_allreduce_add(c, R);
-        }
+        const bool tp = c->p.tp_size > 1;
+        // O projection (+ residual); under TP every rank holds a K slice and the partial products are summed over NVLink
+        if (sk) skinny_linear(c, w.w_o, c->H, c->qd_l, c->attn, c->qd_l, nullptr, c->sk_xq, tp ? c->proj : c->h, c->H, tp ? 0 : 1, R);
+        else gemv(c, w.w_o, c->attn, c->qd_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->qd_l, tp ? 0 : 1, R);
+        if (tp) tp_allreduce_add(c, R);
+        if (sk) skinny_linear(c, w.w_gu, 2 * c->I_l, c->H, c->h, c->H, w.post_norm, c->sk_xh, c->act, c->I_l, 2, R);
+        else gemv(c, w.w_gu, c->h, c->H, c->act, c->I_l, w.post_norm, 2 * c->I_l, c->H, 2, R);
+        if (sk) skinny_linear(c, w.w_down, c->H, c->I_l, c->act, c->I_l, nullptr, c->sk_xi, tp ? c->proj : c->h, c->H, tp ? 0 : 1, R);
+        else gemv(c, w.w_down, c->act, c->I_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->I_l, tp ? 0 : 1, R);
+        if (tp) tp_allreduce_add(c, R);
         if (tap_row0 >= 0) tap_copy(c, l + 1, tap_row0, c->h, R);
     }
     if (tap_row0 >= 0) {
@@ -307,7 +351,8 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         c->launched++;
     }
     if (want_logits) {
-        gemv(c, c->lm_head, c->h, c->H, c->logits, c->V_l, c->final_norm, c->V_l, c->H, 0, R);
+        if (c->skinny_ok && R >= 2 && R <= 16) skinny_linear(c, c->lm_head, c->V_l, c->H, c->h, c->H, c->final_norm, c->sk_xh, c->logits, c->V_l, 0, R);
+        else gemv(c, c->lm_head, c->h, c->H, c->logits, c->V_l, c->final_norm, c->V_l, c->H, 0, R);
         tp_argmax(c, c->logits, R);
     }
 }
@@ -955,6 +1000,7 @@ int b2l_finalize(b2l_ctx* c) {
         B2L_CUDA(cudaDeviceSynchronize());
         ensure_out_ids(c, 256);
         c->pf_ok = c->qkv_l % 128 == 0 && c->H % 128 == 0 && (2 * c->I_l) % 128 == 0 && c->H % 64 == 0 && c->qd_l % 64 == 0 && c->I_l % 64 == 0;
+        skinny_setup(c);
         mega_setup(c);
         c->decode_mode = c->mega_ok ? 1 : 0;
         c->finalized = true;
@@ -1196,6 +1242,7 @@ int b2l_get_info(b2l_ctx* c, b2l_info* out) {
         out->stream_bytes_per_token = per_layer * c->L + 2 * H + 2 * static_cast<int64_t>(c->V_l) * H + 2 * H;
         out->kernels_launched = c->launched;
         out->decode_mode = c->decode_mode;
+        out->batched_tensor_core = c->skinny_ok ? 1 : 0;
         std::snprintf(out->device_name, sizeof(out->device_name), "%s", c->prop.name);
     });
 }

@@ -115,6 +115,13 @@ struct b2l_ctx {
     void* pf_tiles = nullptr;        // device PrefillTile[] (flash prefill attention work list)
     int pf_n_tiles = 0;
 
+    // batched decode on the tensor cores (skinny_gemm.cuh)
+    bool skinny_ok = false;
+    uint16_t *sk_xh = nullptr, *sk_xq = nullptr, *sk_xi = nullptr;   // bf16 hi/lo activation rows [32][K]
+    float* sk_partial = nullptr;                                       // [ksplit][16][N] fp32
+    size_t sk_partial_floats = 0;
+    std::vector<unsigned char> sk_maps;                                // CUtensorMap storage (host): per layer 4 weights + lm_head, then 3 x maps per BT
+
     // tensor parallelism (NCCL, loaded with dlopen only when tp_size > 1)
     void* nccl_comm = nullptr;
     float* tp_pack = nullptr;        // [max_rows][2]   (value, index) of this rank's argmax

@@ -1,0 +1,178 @@
+// skinny_gemm.cuh -- batched-decode projections on the tensor cores.
+// For 2..16 sequences per step a CUDA-core GEMV does 8-16 FMAs per weight element and turns compute
+// bound (measured 1.1 TB/s at batch 8), so the weights go through tcgen05 instead:
+//     Y^T[N][BT] = W[N][K] * X[BT][K]^T        W is the 128-row A operand, X the narrow B operand
+// X carries every activation row TWICE, as bf16 hi and bf16 lo (x = hi + lo to 16 mantissa bits), so
+// the fp32 activations of the decode path keep their accuracy: Y = W hi + W lo.
+// Grid = (N / 128 row tiles) x (K splits): the K split is what gives small matrices (O, down: 16-24
+// row tiles) enough CTAs to pull full HBM bandwidth; partials are summed by skinny_reduce_kernel
+// (deterministic order), which also applies the epilogue (store | residual add | SwiGLU).
+// Same warp roles and TMA/tcgen05 plumbing as gemm_tcgen05.cuh.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace b2l {
+
+constexpr int kSkinnyStages = 5, kSkinnyThreads = 192;   // 5 x 20 KB: two CTAs per SM, the whole grid is one wave
+
+template <int BT>  // columns of the MMA: 2 x (max rows), 16 or 32
+__global__ void __launch_bounds__(kSkinnyThreads, 2)
+skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ partial,
+                   int N, int n_kblocks, int kblocks_per_split) {
+    constexpr uint32_t kStageW = 128 * kGemmBK * 2, kStageX = BT * kGemmBK * 2;   // x tile padded to 4 KB (keeps 1024-byte alignment)
+    static_assert(kStageX <= 4096, "x tile");
+    constexpr uint32_t kStageBytes = kStageW + 4096;
+    extern __shared__ __align__(1024) uint8_t ssm[];
+    const uint32_t base = (smem_u32(ssm) + 1023u) & ~1023u;
+    const uint32_t bars = base + kSkinnyStages * kStageBytes;
+    const uint32_t full = bars, empty = bars + 8 * kSkinnyStages, tmem_full = bars + 16 * kSkinnyStages, tmem_slot = tmem_full + 8;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * 128, split = blockIdx.y;
+    const int kb0 = split * kblocks_per_split, kb1 = min(n_kblocks, kb0 + kblocks_per_split);
+
+    if (tid == 0) {
+        for (int s = 0; s < kSkinnyStages; s++) {
+            mbar_init(full + 8 * s, 1);
+            mbar_init(empty + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(32) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    pdl_launch_dependents();
+    if (warp == 0) {
+        if (lane == 0) {
+            // the weights do not depend on the previous kernel: fill the ring with W tiles before the programmatic
+            // dependency resolves, then add the activation tiles (written by the kernel before this one)
+            const int n_pre = min(kSkinnyStages, kb1 - kb0);
+            for (int i = 0; i < n_pre; i++) {
+                mbar_arrive_expect_tx(full + 8 * i, kStageW + kStageX);
+                tma_load_2d(base + i * kStageBytes, &map_w, (kb0 + i) * kGemmBK, n0, full + 8 * i);
+            }
+            pdl_wait();
+            for (int i = 0; i < n_pre; i++) tma_load_2d(base + i * kStageBytes + kStageW, &map_x, (kb0 + i) * kGemmBK, 0, full + 8 * i);
+            for (int kb = kb0 + n_pre; kb < kb1; kb++) {
+                const int i = kb - kb0, s = i % kSkinnyStages;
+                mbar_wait_spin(empty + 8 * s, ((i / kSkinnyStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(full + 8 * s, kStageW + kStageX);
+                tma_load_2d(base + s * kStageBytes, &map_w, kb * kGemmBK, n0, full + 8 * s);
+                tma_load_2d(base + s * kStageBytes + kStageW, &map_x, kb * kGemmBK, 0, full + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BT);
+            for (int kb = kb0; kb < kb1; kb++) {
+                const int i = kb - kb0, s = i % kSkinnyStages;
+                mbar_wait_spin(full + 8 * s, (i / kSkinnyStages) & 1);
+                tcgen05_fence_after();
+                const uint64_t da = umma_smem_desc(base + s * kStageBytes), db = umma_smem_desc(base + s * kStageBytes + kStageW);
+#pragma unroll
+                for (int k = 0; k < kGemmBK / 16; k++) umma_bf16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (i | k) != 0);
+                tcgen05_commit(empty + 8 * s);
+            }
+            tcgen05_commit(tmem_full);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = n0 + quarter * 32 + lane;   // TMEM lane = weight row
+        pdl_wait();   // `partial` is still being read by the reduce of the previous projection until then
+        mbar_wait_spin(tmem_full, 0);
+        tcgen05_fence_after();
+        constexpr int T = BT / 2;                    // token rows: column t = hi part, column t + T = lo part
+        float v[BT];
+#pragma unroll
+        for (int c0 = 0; c0 < BT; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, r);
+#pragma unroll
+            for (int j = 0; j < 16; j++) v[c0 + j] = __uint_as_float(r[j]);
+        }
+        if (row < N) {
+#pragma unroll
+            for (int t = 0; t < T; t++) partial[(static_cast<size_t>(split) * T + t) * N + row] = v[t] + v[t + T];
+        }
+        tcgen05_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+    }
+}
+
+// y (op)= sum over K splits of partial[split][t][n];  mode 0 store, 1 += (residual), 2 SwiGLU over (2i, 2i+1)
+__global__ void skinny_reduce_kernel(const float* __restrict__ partial, int ksplit, int T, int N, int R, int mode,
+                                     float* __restrict__ y, int ldy) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = blockIdx.y;
+    if (t >= R) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode == 2) {
+        if (2 * i + 1 >= N) return;
+        float g = 0.f, u = 0.f;
+        for (int s = 0; s < ksplit; s++) {
+            const float2 p = *reinterpret_cast<const float2*>(partial + (static_cast<size_t>(s) * T + t) * N + 2 * i);
+            g += p.x;
+            u += p.y;
+        }
+        y[static_cast<size_t>(t) * ldy + i] = (g / (1.0f + __expf(-g))) * u;
+    } else {
+        if (i >= N) return;
+        float acc = 0.f;
+        for (int s = 0; s < ksplit; s++) acc += partial[(static_cast<size_t>(s) * T + t) * N + i];
+        float* dst = y + static_cast<size_t>(t) * ldy + i;
+        *dst = mode == 1 ? *dst + acc : acc;
+    }
+}
+
+// fp32 rows -> bf16 (hi, lo) rows for the B operand; NORM: fused RMSNorm. out is [2*T][K]: row r = hi, row T + r = lo
+template <bool NORM>
+__global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, const uint16_t* __restrict__ w, uint16_t* __restrict__ out,
+                                  int K, int T, float eps) {
+    __shared__ float s_red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.x;
+    const float* xr = x + static_cast<size_t>(r) * ldx;
+    float inv = 1.f;
+    if (NORM) {
+        float ss = 0.f;
+        for (int i = threadIdx.x * 4; i < K; i += blockDim.x * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(xr + i);
+            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        ss = warp_sum(ss);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int i = 0; i < (blockDim.x >> 5); i++) tot += s_red[i];
+        inv = rsqrtf(tot / static_cast<float>(K) + eps);
+    }
+    for (int i = threadIdx.x * 4; i < K; i += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(xr + i);
+        if (NORM) {
+            const uint2 nw = *reinterpret_cast<const uint2*>(w + i);
+            v.x = bf16lo(nw.x) * (v.x * inv); v.y = bf16hi(nw.x) * (v.y * inv);
+            v.z = bf16lo(nw.y) * (v.z * inv); v.w = bf16hi(nw.y) * (v.w * inv);
+        }
+        const uint16_t h0 = f32_to_bf16_bits(v.x), h1 = f32_to_bf16_bits(v.y), h2 = f32_to_bf16_bits(v.z), h3 = f32_to_bf16_bits(v.w);
+        const float l0 = v.x - bf16_bits_to_f32(h0), l1 = v.y - bf16_bits_to_f32(h1), l2 = v.z - bf16_bits_to_f32(h2), l3 = v.w - bf16_bits_to_f32(h3);
+        *reinterpret_cast<uint2*>(out + static_cast<size_t>(r) * K + i) =
+            make_uint2(static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16), static_cast<uint32_t>(h2) | (static_cast<uint32_t>(h3) << 16));
+        *reinterpret_cast<uint2*>(out + static_cast<size_t>(T + r) * K + i) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+}
+
+}  // namespace b2l

@@ -186,6 +186,33 @@ def test_batched_decode_ragged_lengths_matches_per_sequence_oracle():
         assert ids[:, i].tolist() == oids[1:].tolist(), (i, float(margins.min()))
 
 
+@pytest.mark.parametrize("n_seq", [5, 12])
+def test_batched_decode_on_tensor_cores_matches_per_sequence_oracle(n_seq):
+    """2..16 rows per step: projections run as tcgen05 skinny GEMMs (hi/lo bf16 split of the fp32 activations)."""
+    po = _po()
+    arch, tensors = synth_tensors("1b", 2, 5)
+    lens = [(7 * i + 3) % 40 + 1 for i in range(n_seq)]
+    prompts = [synth.synth_prompt(n, arch.vocab_size, arch.bos_token_id, 300 + i) for i, n in enumerate(lens)]
+    eng = make_engine(arch, tensors, max_batch=n_seq, max_positions=64, max_prefill_tokens=64 * n_seq)
+    assert eng.info().batched_tensor_core == 1
+    eng.set_prefill_mode(0)
+    bt = contiguous_tables(n_seq, eng.max_blocks)
+    first = eng.prefill(prompts, [0] * n_seq, bt)
+    ids, _ = eng.decode_loop(first, lens, bt, 6)
+    last_logits = eng.logits(0, n_seq).copy()
+    om = po.OracleModel(arch, tensors, 64)
+    for i, p in enumerate(prompts):
+        seq = om.seq(po.ORC_KV_BF16)
+        oids, margins = seq.greedy(p, 7)
+        assert int(first[i]) == int(oids[0]), i
+        assert ids[:, i].tolist() == oids[1:].tolist(), (i, float(margins.min()))
+        # logits of the last decode step against the oracle's (fp32 activations on both sides)
+        seq.reset()
+        ol, _ = seq.forward(np.concatenate([p, oids[:6]]).astype(np.int32))
+        assert np.abs(last_logits[i] - ol[0]).max() < 5e-3, (i, float(np.abs(last_logits[i] - ol[0]).max()))
+    eng.close()
+
+
 def test_chunked_prefill_continues_a_cached_sequence():
     arch, tensors = synth_tensors("tiny", None, 1234)
     prompt = synth.synth_prompt(30, arch.vocab_size, arch.bos_token_id, 8)
