@@ -34,7 +34,7 @@ class B2lInfo(C.Structure):
         ("abi_version", C.c_int32), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
         ("hbm_bytes", C.c_int64), ("weight_bytes", C.c_int64), ("kv_bytes", C.c_int64),
         ("stream_bytes_per_token", C.c_int64), ("kernels_launched", C.c_int64), ("decode_mode", C.c_int32),
-        ("batched_tensor_core", C.c_int32),
+        ("batched_tensor_core", C.c_int32), ("tp_transport", C.c_int32),
         ("device_name", C.c_char * 64),
     ]
 

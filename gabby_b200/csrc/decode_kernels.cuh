@@ -37,6 +37,22 @@ __global__ void embed_kernel(const uint16_t* __restrict__ E, const int32_t* __re
 // One warp owns two weight rows at a time (the pair, in MODE 2) and streams them with 128-bit
 // L1-bypassing loads; x lives in shared memory as fp32 in K-tiles of `kt` elements.
 // ------------------------------------------------------------------------------------------
+// Tensor-parallel partial sums go straight into every rank's receive slab over NVLink peer memory, as 8-byte
+// {value bits, sequence number} words (the "LL" idea: the flag travels with the data, an 8-byte store is atomic,
+// so the receiver needs no fence and no separate signal -- it polls the word until the sequence number matches).
+constexpr int kTpMaxRanks = 8;
+struct TpSend {
+    uint2* dst[kTpMaxRanks];   // per rank (self included): that rank's slab for (slot, this rank), [rows_cap][H]
+    const uint32_t* seq;       // this rank's sequence number for the slot (device memory; bumped by the receiver kernel)
+    int tp;
+};
+__device__ __forceinline__ void tp_send_pair(const TpSend& t, size_t idx, float v0, float v1, uint32_t seq) {
+    // idx even: two adjacent outputs = one 16-byte store per peer (each 8-byte half is self-describing)
+    for (int p = 0; p < t.tp; p++)
+        asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(t.dst[p] + idx), "r"(__float_as_uint(v0)), "r"(seq),
+                     "r"(__float_as_uint(v1)), "r"(seq) : "memory");
+}
+
 struct GemvArgs {
     const uint16_t* W;       // [N][K] bf16
     const float* x;          // [B][ldx]
@@ -45,6 +61,7 @@ struct GemvArgs {
     const float* add;        // optional [B][ldadd]: x <- x + add before use (TP partial-sum fold), may be null
     float eps;
     int N, K, ldx, ldy, kt;
+    TpSend tps;              // MODE 3 only
 };
 
 constexpr int kGemvThreads = 256;
@@ -60,6 +77,8 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvArgs a) {
 
     pdl_launch_dependents();
     pdl_wait();
+    uint32_t tp_seq = 0;
+    if (MODE == 3) tp_seq = *reinterpret_cast<const volatile uint32_t*>(a.tps.seq);
 
     if (NORM) {
         // LlamaRMSNorm: inv = rsqrt(mean(x^2) + eps)            (oracle: rmsnorm())
@@ -142,7 +161,10 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvArgs a) {
             const float s0 = warp_sum(acc0[b]);
             const float s1 = warp_sum(acc1[b]);
             if (lane == 0 && live) {
-                if (MODE == 2) {
+                if (MODE == 3) {
+                    // row-parallel projection under TP: this rank's partial sum goes to every rank over NVLink
+                    tp_send_pair(a.tps, static_cast<size_t>(b) * a.ldy + row0, s0, s1, tp_seq);
+                } else if (MODE == 2) {
                     // silu(gate) * up                               (oracle: MLP block)
                     a.y[static_cast<size_t>(b) * a.ldy + (row0 >> 1)] = (s0 / (1.0f + __expf(-s0))) * s1;
                 } else if (MODE == 1) {
@@ -434,6 +456,49 @@ __global__ void add_kernel(float* __restrict__ y, const float* __restrict__ x, i
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
+}
+
+// TP receiver: h += sum over ranks (rank order: identical bits on every rank) of the partial sums that arrive in this
+// rank's slab recv[src][rows_cap][H]; bumps the slot's sequence number when the whole grid is done.
+__global__ void tp_ll_reduce_kernel(float* __restrict__ h, const uint2* recv, int tp, int R, int H, int rows_cap,
+                                    uint32_t* seq, unsigned int* done) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t want = *reinterpret_cast<volatile uint32_t*>(seq);
+    const int half = H >> 1, n_pairs = R * half;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+        const int r = i / half, n = (i - r * half) * 2;
+        float s0 = 0.f, s1 = 0.f;
+        for (int src = 0; src < tp; src++) {
+            const uint2* p = recv + (static_cast<size_t>(src) * rows_cap + r) * H + n;
+            uint32_t v0, q0, v1, q1;
+            long long t0 = 0;
+            for (unsigned spin = 0;; spin++) {
+                asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(q0), "=r"(v1), "=r"(q1) : "l"(p) : "memory");
+                if (q0 == want && q1 == want) break;
+                if ((spin & 1023u) == 1023u) {            // a peer that never sends must not hang the GPU
+                    const long long now = clock64();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 120000000000ll) __trap();   // ~60 s
+                }
+            }
+            s0 += __uint_as_float(v0);
+            s1 += __uint_as_float(v1);
+        }
+        float2* dst = reinterpret_cast<float2*>(h + static_cast<size_t>(r) * H + n);
+        float2 cur = *dst;
+        cur.x += s0;
+        cur.y += s1;
+        *dst = cur;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {
+            *done = 0;
+            *reinterpret_cast<volatile uint32_t*>(seq) = want + 1;
+        }
+    }
 }
 
 // TP greedy argmax: pack this rank's (max value, global index) per row for the all-gather ...

@@ -199,6 +199,8 @@ void gemv_launch(b2l_ctx* c, GemvArgs a, int R) {
         GemvArgs g = a;
         g.x = a.x + static_cast<size_t>(r0) * a.ldx;
         g.y = a.y + static_cast<size_t>(r0) * a.ldy;
+        if (MODE == 3)
+            for (int p = 0; p < a.tps.tp; p++) g.tps.dst[p] = a.tps.dst[p] + static_cast<size_t>(r0) * a.ldy;
         const int B = n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : 8;
         g.kt = gemv_kt(B, a.K);
         switch (B) {
@@ -211,9 +213,15 @@ void gemv_launch(b2l_ctx* c, GemvArgs a, int R) {
 }
 
 void gemv(b2l_ctx* c, const uint16_t* W, const float* x, int ldx, float* y, int ldy, const uint16_t* norm_w, int N,
-          int K, int mode, int R) {
+          int K, int mode, int R, const TpSend* tps = nullptr) {
     B2L_CHECK(K % 8 == 0 && N % 2 == 0, "gemv: K must be a multiple of 8 and N even");
-    GemvArgs a{W, x, y, norm_w, nullptr, c->p.rms_norm_eps, N, K, ldx, ldy, 0};
+    GemvArgs a{W, x, y, norm_w, nullptr, c->p.rms_norm_eps, N, K, ldx, ldy, 0, TpSend{}};
+    if (mode == 3) {
+        B2L_CHECK(tps && !norm_w, "gemv: TP send needs peers and no fused norm");
+        a.tps = *tps;
+        gemv_launch<3, false>(c, a, R);
+        return;
+    }
     if (norm_w) {
         if (mode == 0) gemv_launch<0, true>(c, a, R);
         else if (mode == 2) gemv_launch<2, true>(c, a, R);
@@ -279,7 +287,7 @@ void skinny_setup(b2l_ctx* c) {
 
 // y (op)= W x for R (2..16) activation rows: prep (hi/lo bf16 [+ RMSNorm]) -> tcgen05 skinny GEMM -> split reduce + epilogue
 void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, int ldx, const uint16_t* norm_w, uint16_t* xbuf,
-                   float* y, int ldy, int mode, int R) {
+                   float* y, int ldy, int mode, int R, const TpSend* tps = nullptr) {
     const int BT = R <= 8 ? 16 : 32, T = BT / 2;
     if (norm_w) launch(c, split_bf16_kernel<true>, dim3(R), dim3(256), 0, x, ldx, norm_w, xbuf, K, T, c->p.rms_norm_eps);
     else launch(c, split_bf16_kernel<false>, dim3(R), dim3(256), 0, x, ldx, static_cast<const uint16_t*>(nullptr), xbuf, K, T, 0.f);
@@ -295,7 +303,95 @@ void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, 
     if (BT == 16) launch(c, skinny_gemm_kernel<16>, grid, dim3(kSkinnyThreads), smem, mw, mx, c->sk_partial, N, n_kblocks, per_split);
     else launch(c, skinny_gemm_kernel<32>, grid, dim3(kSkinnyThreads), smem, mw, mx, c->sk_partial, N, n_kblocks, per_split);
     const int cols = mode == 2 ? N / 2 : N;
-    launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, y, ldy);
+    launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, y, ldy,
+           tps ? *tps : TpSend{});
+}
+
+// ---- TP over peer memory: the projection kernel's epilogue stores its partial sums into every rank's slab,
+// the receiver kernel adds them into the residual stream. No collective call, no separate all-reduce kernel. ----
+TpSend tp_send_args(const b2l_ctx* c, int slot) {
+    TpSend t{};
+    t.tp = c->p.tp_size;
+    t.seq = c->tp_seq + slot;
+    const size_t slab = static_cast<size_t>(c->max_rows) * c->H;
+    for (int p = 0; p < t.tp; p++) t.dst[p] = c->tp_peer[p] + (static_cast<size_t>(slot) * t.tp + c->p.tp_rank) * slab;
+    return t;
+}
+void tp_ll_reduce(b2l_ctx* c, int slot, int R) {
+    const int n_pairs = R * c->H / 2;
+    const int grid = std::max(1, std::min((n_pairs + 255) / 256, c->prop.multiProcessorCount));
+    const uint2* recv = c->tp_ll + static_cast<size_t>(slot) * c->p.tp_size * c->max_rows * c->H;
+    launch(c, tp_ll_reduce_kernel, dim3(grid), dim3(256), 0, c->h, recv, c->p.tp_size, R, c->H, c->max_rows, c->tp_seq + slot, c->tp_done + slot);
+}
+
+// Map every rank's receive slab into this process (cudaIpc; handles travel through one NCCL all-gather).
+// Collective: called by every rank from b2l_create. B2L_TP_TRANSPORT=nccl keeps the NCCL all-reduce instead.
+void tp_peer_setup(b2l_ctx* c) {
+    const int tp = c->p.tp_size, rank = c->p.tp_rank;
+    const char* env = std::getenv("B2L_TP_TRANSPORT");
+    const bool want = !(env && std::string(env) == "nccl") && tp <= kTpMaxRanks;
+    const size_t words = static_cast<size_t>(2) * tp * c->max_rows * c->H;
+    c->tp_ll = dalloc<uint2>(c, words);
+    B2L_CUDA(cudaMemset(c->tp_ll, 0, words * sizeof(uint2)));      // sequence 0 is never sent
+    c->tp_seq = dalloc<uint32_t>(c, 2);
+    c->tp_done = dalloc<unsigned int>(c, 2);
+    const uint32_t ones[2] = {1, 1};
+    B2L_CUDA(cudaMemcpy(c->tp_seq, ones, sizeof(ones), cudaMemcpyHostToDevice));
+    B2L_CUDA(cudaMemset(c->tp_done, 0, 2 * sizeof(unsigned int)));
+    // every rank takes part in the exchange even if it will not use the result, so the collective matches
+    constexpr size_t kSlot = 80;   // 64-byte handle + ok flag, padded to a multiple of 16
+    static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "ipc handle size");
+    std::vector<unsigned char> mine(kSlot, 0), all(kSlot * tp, 0);
+    cudaIpcMemHandle_t hd;
+    const cudaError_t ge = want ? cudaIpcGetMemHandle(&hd, c->tp_ll) : cudaErrorNotSupported;
+    if (ge == cudaSuccess) {
+        std::memcpy(mine.data(), &hd, sizeof(hd));
+        mine[64] = 1;
+    } else {
+        cudaGetLastError();
+    }
+    unsigned char* d_ex = dalloc<unsigned char>(c, kSlot * (tp + 1));
+    B2L_CUDA(cudaMemcpy(d_ex, mine.data(), kSlot, cudaMemcpyHostToDevice));
+    B2L_NCCL(nccl().AllGather(d_ex, d_ex + kSlot, kSlot / 4, kNcclFloat32, c->nccl_comm, c->stream));
+    B2L_CUDA(cudaStreamSynchronize(c->stream));
+    B2L_CUDA(cudaMemcpy(all.data(), d_ex + kSlot, kSlot * tp, cudaMemcpyDeviceToHost));
+    bool ok = true;
+    for (int p = 0; p < tp; p++) ok = ok && all[p * kSlot + 64] == 1;
+    int opened = 0;
+    if (ok) {
+        for (int p = 0; p < tp && ok; p++) {
+            if (p == rank) {
+                c->tp_peer[p] = c->tp_ll;
+                continue;
+            }
+            cudaIpcMemHandle_t ph;
+            std::memcpy(&ph, all.data() + p * kSlot, sizeof(ph));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, ph, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+                break;
+            }
+            c->tp_peer[p] = static_cast<uint2*>(ptr);
+            opened++;
+        }
+    }
+    // all ranks must agree on the transport: one more tiny exchange of the outcome
+    float* d_ok = reinterpret_cast<float*>(d_ex);
+    const float mine_ok = ok ? 0.f : 1.f;
+    B2L_CUDA(cudaMemcpy(d_ok, &mine_ok, sizeof(float), cudaMemcpyHostToDevice));
+    B2L_NCCL(nccl().AllReduce(d_ok, d_ok, 1, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream));
+    B2L_CUDA(cudaStreamSynchronize(c->stream));
+    float failures = 0.f;
+    B2L_CUDA(cudaMemcpy(&failures, d_ok, sizeof(float), cudaMemcpyDeviceToHost));
+    c->tp_peer_ok = failures == 0.f;
+    if (!c->tp_peer_ok) {
+        for (int p = 0; p < tp; p++) {
+            if (p != rank && c->tp_peer[p]) cudaIpcCloseMemHandle(c->tp_peer[p]);
+            c->tp_peer[p] = nullptr;
+        }
+    }
+    (void)opened;
 }
 
 // h += all_reduce_sum(proj) over the TP ranks (fp32; the messages are R x H x 4 bytes: latency-bound)
@@ -335,14 +431,19 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         attn_launch(c, aa, R);
         const bool tp = c->p.tp_size > 1;
         // O projection (+ residual); under TP every rank holds a K slice and the partial products are summed over NVLink
-        if (sk) skinny_linear(c, w.w_o, c->H, c->qd_l, c->attn, c->qd_l, nullptr, c->sk_xq, tp ? c->proj : c->h, c->H, tp ? 0 : 1, R);
-        else gemv(c, w.w_o, c->attn, c->qd_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->qd_l, tp ? 0 : 1, R);
-        if (tp) tp_allreduce_add(c, R);
+        const bool peer = tp && c->tp_peer_ok;
+        const TpSend send0 = peer ? tp_send_args(c, 0) : TpSend{}, send1 = peer ? tp_send_args(c, 1) : TpSend{};
+        const int omode = peer ? 3 : tp ? 0 : 1;
+        if (sk) skinny_linear(c, w.w_o, c->H, c->qd_l, c->attn, c->qd_l, nullptr, c->sk_xq, tp ? c->proj : c->h, c->H, omode, R, &send0);
+        else gemv(c, w.w_o, c->attn, c->qd_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->qd_l, omode, R, &send0);
+        if (peer) tp_ll_reduce(c, 0, R);
+        else if (tp) tp_allreduce_add(c, R);
         if (sk) skinny_linear(c, w.w_gu, 2 * c->I_l, c->H, c->h, c->H, w.post_norm, c->sk_xh, c->act, c->I_l, 2, R);
         else gemv(c, w.w_gu, c->h, c->H, c->act, c->I_l, w.post_norm, 2 * c->I_l, c->H, 2, R);
-        if (sk) skinny_linear(c, w.w_down, c->H, c->I_l, c->act, c->I_l, nullptr, c->sk_xi, tp ? c->proj : c->h, c->H, tp ? 0 : 1, R);
-        else gemv(c, w.w_down, c->act, c->I_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->I_l, tp ? 0 : 1, R);
-        if (tp) tp_allreduce_add(c, R);
+        if (sk) skinny_linear(c, w.w_down, c->H, c->I_l, c->act, c->I_l, nullptr, c->sk_xi, tp ? c->proj : c->h, c->H, omode, R, &send1);
+        else gemv(c, w.w_down, c->act, c->I_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->I_l, omode, R, &send1);
+        if (peer) tp_ll_reduce(c, 1, R);
+        else if (tp) tp_allreduce_add(c, R);
         if (tap_row0 >= 0) tap_copy(c, l + 1, tap_row0, c->h, R);
     }
     if (tap_row0 >= 0) {
@@ -894,6 +995,7 @@ int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_
             NcclApi::Id id;
             std::memcpy(id.internal, nccl_unique_id, B2L_NCCL_ID_BYTES);
             B2L_NCCL(nccl().CommInitRank(&c->nccl_comm, tp, id, p->tp_rank));   // collective: every rank is in b2l_create now
+            tp_peer_setup(c);
         }
         B2L_CUDA(cudaDeviceSynchronize());
         *out = c;
@@ -913,6 +1015,13 @@ void b2l_destroy(b2l_ctx* c) {
     for (auto& kv : c->decode_graphs) {
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    if (c->tp_peer_ok && c->nccl_comm) {
+        // nobody may free a slab a peer can still write to: meet once more, then unmap
+        float* d = reinterpret_cast<float*>(c->tp_done);
+        if (nccl().AllReduce(d, d, 1, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream) == 0) cudaStreamSynchronize(c->stream);
+        for (int p = 0; p < c->p.tp_size; p++)
+            if (p != c->p.tp_rank && c->tp_peer[p]) cudaIpcCloseMemHandle(c->tp_peer[p]);
     }
     if (c->nccl_comm) nccl().CommDestroy(c->nccl_comm);
     for (void* p : c->allocs) cudaFree(p);
@@ -1002,6 +1111,12 @@ int b2l_finalize(b2l_ctx* c) {
         c->pf_ok = c->qkv_l % 128 == 0 && c->H % 128 == 0 && (2 * c->I_l) % 128 == 0 && c->H % 64 == 0 && c->qd_l % 64 == 0 && c->I_l % 64 == 0;
         skinny_setup(c);
         mega_setup(c);
+        if (c->p.tp_size > 1) {
+            // ranks load at different speeds: meet here so that the first forward starts roughly together
+            float* d = reinterpret_cast<float*>(c->tp_done);
+            B2L_NCCL(nccl().AllReduce(d, d, 1, kNcclFloat32, kNcclSum, c->nccl_comm, c->stream));
+            B2L_CUDA(cudaStreamSynchronize(c->stream));
+        }
         c->decode_mode = c->mega_ok ? 1 : 0;
         c->finalized = true;
     });
@@ -1243,6 +1358,7 @@ int b2l_get_info(b2l_ctx* c, b2l_info* out) {
         out->kernels_launched = c->launched;
         out->decode_mode = c->decode_mode;
         out->batched_tensor_core = c->skinny_ok ? 1 : 0;
+        out->tp_transport = c->p.tp_size == 1 ? 0 : c->tp_peer_ok ? 2 : 1;
         std::snprintf(out->device_name, sizeof(out->device_name), "%s", c->prop.name);
     });
 }

@@ -128,6 +128,12 @@ struct b2l_ctx {
     float* tp_gather = nullptr;      // [tp][max_rows][2]
     float* tp_logits = nullptr;      // [tp][rows][V_l] gather buffer for b2l_get_logits (lazy)
     float* tp_vals = nullptr;        // [max_rows] local max values
+    // row-parallel partial sums over NVLink peer memory (cudaIpc-mapped slabs, LL words): see TpSend
+    bool tp_peer_ok = false;         // false: NCCL all-reduce transport
+    uint2* tp_ll = nullptr;          // this rank's slabs [2 slots][tp][max_rows][H]
+    uint2* tp_peer[8] = {};          // every rank's slab base as mapped here (own = tp_ll)
+    uint32_t* tp_seq = nullptr;      // [2] sequence number per slot
+    unsigned int* tp_done = nullptr; // [2] last-CTA counters of the receiver kernel
 
     std::map<int, b2l::Graph> decode_graphs;  // key: rows (+ 1000 when the loop variant with advance)
     int64_t launched = 0;

@@ -10,6 +10,7 @@
 // Same warp roles and TMA/tcgen05 plumbing as gemm_tcgen05.cuh.
 #pragma once
 #include "gemm_tcgen05.cuh"
+#include "decode_kernels.cuh"
 
 namespace b2l {
 
@@ -111,15 +112,26 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     }
 }
 
-// y (op)= sum over K splits of partial[split][t][n];  mode 0 store, 1 += (residual), 2 SwiGLU over (2i, 2i+1)
+// y (op)= sum over K splits of partial[split][t][n];  mode 0 store, 1 += (residual), 2 SwiGLU over (2i, 2i+1),
+// 3 = send the sums to every TP rank (tp_send_pair)
 __global__ void skinny_reduce_kernel(const float* __restrict__ partial, int ksplit, int T, int N, int R, int mode,
-                                     float* __restrict__ y, int ldy) {
+                                     float* __restrict__ y, int ldy, const TpSend tps) {
     pdl_launch_dependents();
     pdl_wait();
     const int t = blockIdx.y;
     if (t >= R) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mode == 2) {
+    if (mode == 3) {
+        if (2 * i + 1 >= N) return;
+        const uint32_t seq = *reinterpret_cast<const volatile uint32_t*>(tps.seq);
+        float a0 = 0.f, a1 = 0.f;
+        for (int s = 0; s < ksplit; s++) {
+            const float2 p = *reinterpret_cast<const float2*>(partial + (static_cast<size_t>(s) * T + t) * N + 2 * i);
+            a0 += p.x;
+            a1 += p.y;
+        }
+        tp_send_pair(tps, static_cast<size_t>(t) * ldy + 2 * i, a0, a1, seq);
+    } else if (mode == 2) {
         if (2 * i + 1 >= N) return;
         float g = 0.f, u = 0.f;
         for (int s = 0; s < ksplit; s++) {

@@ -123,6 +123,7 @@ typedef struct {
     int64_t kernels_launched;  /* kernels this ctx has launched so far (graph nodes count) */
     int32_t decode_mode;       /* 0 = multi-kernel graph, 1 = persistent megakernel */
     int32_t batched_tensor_core; /* 1: decode steps of 2..16 rows run their projections on tcgen05 (skinny GEMM) */
+    int32_t tp_transport;      /* 0 = single rank, 1 = NCCL all-reduce, 2 = fused stores into NVLink peer memory (cudaIpc slabs) */
     char device_name[64];
 } b2l_info;
 int b2l_get_info(b2l_ctx* c, b2l_info* out);

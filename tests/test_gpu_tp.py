@@ -1,4 +1,4 @@
-"""Tensor-parallel parity (needs >= 2 GPUs; run with `gpurun --gpus 2`): TP=2 over NCCL against the
+"""Tensor-parallel parity (needs >= 2 GPUs; run with `gpurun --gpus 2`): TP=2 (fused peer-memory stores, and the NCCL all-reduce transport) against the
 CPU oracle and against TP=1. Sum order differs across ranks, so logits carry a tolerance; greedy ids
 and argmax indices must be identical."""
 import multiprocessing as mp
@@ -17,8 +17,11 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("preset,layers,seed", [("tiny128", None, 77), ("tiny", None, 1234)])
-def test_tp2_matches_oracle_and_single_gpu(preset, layers, seed):
+@pytest.mark.parametrize("preset,layers,seed,transport", [
+    ("tiny128", None, 77, "peer"), ("tiny", None, 1234, "peer"), ("tiny128", None, 77, "nccl"),
+    ("1b", 2, 5, "peer"),      # full 1B width: batch 2 runs the tcgen05 skinny GEMMs, whose reduce kernel does the sends
+])
+def test_tp2_matches_oracle_and_single_gpu(preset, layers, seed, transport):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     from gabby_b200 import _capi
@@ -30,7 +33,7 @@ def test_tp2_matches_oracle_and_single_gpu(preset, layers, seed):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     nccl_id = _capi.nccl_unique_id()
-    procs = [ctx.Process(target=tp_worker.run, args=(r, world, nccl_id, preset, layers, seed, prompts, n_new, 2, q)) for r in range(world)]
+    procs = [ctx.Process(target=tp_worker.run, args=(r, world, nccl_id, preset, layers, seed, prompts, n_new, 2, q, transport)) for r in range(world)]
     for p in procs:
         p.start()
     results = {}
@@ -44,6 +47,8 @@ def test_tp2_matches_oracle_and_single_gpu(preset, layers, seed):
     assert r0[2] == r1[2] and r0[3] == r1[3]                       # every rank sees the same tokens
     assert np.array_equal(r0[4], r1[4]) and np.array_equal(r0[5], r1[5])
     assert r0[7] == 0                                              # TP runs the multi-kernel path
+    # 2 = partial sums stored straight into the peers' slabs over NVLink (no all-reduce call), 1 = NCCL all-reduce
+    assert r0[8] == r1[8] == (2 if transport == "peer" else 1), (r0[8], r1[8])
     om = po.OracleModel(arch, tensors, 256)
     for i, prompt in enumerate(prompts):
         s = om.seq(po.ORC_KV_BF16)

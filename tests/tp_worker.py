@@ -9,8 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(rank, world, nccl_id, preset, layers, seed, prompt, n_new, max_batch, out_q):
+def run(rank, world, nccl_id, preset, layers, seed, prompt, n_new, max_batch, out_q, transport="peer"):
     try:
+        os.environ["B2L_TP_TRANSPORT"] = transport
         from gabby_b200 import _capi, _host, synth
         arch = synth.preset(preset, layers)
         eng = _capi.Engine(arch, _host.rope_table(arch, 256), max_batch=max_batch, max_positions=256, max_prefill_tokens=128,
@@ -28,7 +29,7 @@ def run(rank, world, nccl_id, preset, layers, seed, prompt, n_new, max_batch, ou
         ids, ms = eng.decode_loop(first, [len(p) for p in prompt], bt, n_new)
         logits1 = eng.logits(0, n_seq)
         info = eng.info()
-        out_q.put((rank, "ok", first.tolist(), ids.tolist(), logits0, logits1, int(info.weight_bytes), int(info.decode_mode)))
+        out_q.put((rank, "ok", first.tolist(), ids.tolist(), logits0, logits1, int(info.weight_bytes), int(info.decode_mode), int(info.tp_transport)))
         eng.close()
     except Exception as e:  # noqa: BLE001
         out_q.put((rank, "error", repr(e)))
