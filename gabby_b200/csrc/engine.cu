@@ -665,18 +665,36 @@ void mega_setup(b2l_ctx* c) {
     if (stages < 8) return no("not enough shared memory for the weight ring");
     c->mega_stages = stages;
     c->mega_smem = static_cast<size_t>(stages) * kMegaStageBytes + fixed;
-    B2L_CUDA(cudaFuncSetAttribute(mega_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->mega_smem)));
-    {   // the kernel calls non-inlined device functions: make sure the per-thread stack covers its frames
+    if (const char* e = std::getenv("B2L_MEGA_LL")) c->mega_ll = std::atoi(e) != 0;
+    for (int v = 0; v < 2; v++) {
+        auto kern = v ? mega_decode_kernel<true> : mega_decode_kernel<false>;
+        B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->mega_smem)));
+        // the kernel calls non-inlined device functions: make sure the per-thread stack covers its frames
         cudaFuncAttributes fa{};
-        B2L_CUDA(cudaFuncGetAttributes(&fa, mega_decode_kernel));
+        B2L_CUDA(cudaFuncGetAttributes(&fa, kern));
         size_t cur = 0;
         B2L_CUDA(cudaDeviceGetLimit(&cur, cudaLimitStackSize));
         const size_t want = static_cast<size_t>(fa.localSizeBytes) + 2048;
         if (cur < want) B2L_CUDA(cudaDeviceSetLimit(cudaLimitStackSize, want));
+        int per_sm = 0;
+        B2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kMegaThreads, c->mega_smem));
+        if (per_sm < 1) return no("megakernel does not fit on an SM");
     }
-    int per_sm = 0;
-    B2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel, kMegaThreads, c->mega_smem));
-    if (per_sm < 1) return no("megakernel does not fit on an SM");
+    {   // dataflow buffers; sequence number 0 (the memset) is never produced
+        const size_t n_part = static_cast<size_t>(c->nkv_l) * c->mega_nsplit * c->group;
+        auto zalloc = [&](size_t words) {
+            unsigned long long* p = dalloc<unsigned long long>(c, words);
+            B2L_CUDA(cudaMemset(p, 0, words * sizeof(unsigned long long)));
+            return p;
+        };
+        c->mega_ll_h = zalloc(c->H);
+        c->mega_ll_qkv = zalloc(c->qkv_l);
+        c->mega_ll_act = zalloc(c->I_l);
+        c->mega_ll_pacc = zalloc(n_part * c->hd);
+        c->mega_ll_pml = zalloc(n_part * 2);
+        c->mega_ll_keys = zalloc(static_cast<size_t>(2) * G);
+        c->mega_seq = 0;
+    }
     MegaPhase* d = dalloc<MegaPhase>(c, ph.size());
     B2L_CUDA(cudaMemcpy(d, ph.data(), sizeof(MegaPhase) * ph.size(), cudaMemcpyHostToDevice));
     c->mega_phases = d;
@@ -717,6 +735,10 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     a.part_acc = c->part_acc; a.part_ml = c->part_ml; a.attn_counters = c->attn_counters; a.nsplit_max = c->mega_nsplit;
     a.token = c->d_tokens; a.position = c->d_positions; a.out_ids = c->d_out_ids; a.n_steps = n_steps;
     a.bar_counter = c->mega_bar; a.bar_epoch = c->mega_bar + 1; a.argmax_keys = c->mega_bar + 2;
+    a.ll_h = c->mega_ll_h; a.ll_qkv = c->mega_ll_qkv; a.ll_act = c->mega_ll_act; a.ll_pacc = c->mega_ll_pacc;
+    a.ll_pml = c->mega_ll_pml; a.ll_keys = c->mega_ll_keys;
+    a.seq_base = c->mega_seq;
+    if (c->mega_ll) c->mega_seq += static_cast<uint32_t>(n_steps) * static_cast<uint32_t>(c->mega_n_phases);
     int* dev_abort = nullptr;
     B2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_abort), c->mega_abort, 0));
     a.abort_flag = dev_abort;
@@ -749,7 +771,8 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
         cfg.numAttrs = 2;
     }
     B2L_CUDA(cudaMemcpyToSymbolAsync(c_mega, &a, sizeof(MegaArgs), 0, cudaMemcpyHostToDevice, c->stream));
-    B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel));
+    if (c->mega_ll) B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel<true>));
+    else B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel<false>));
     c->launched++;
 }
 

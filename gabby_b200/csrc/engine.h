@@ -101,6 +101,11 @@ struct b2l_ctx {
     size_t mega_l2_persist_bytes = 0;
     int mega_inflight = 0, mega_l2_ahead = 0, mega_attn_tps = 128;
     unsigned long long *mega_bar = nullptr;  // [0] counter, [1] epoch, [2..4] argmax keys
+    // dataflow mode: {value, seq} word buffers (h | qkv | act | attention partials | per-CTA argmax keys)
+    bool mega_ll = true;
+    unsigned long long *mega_ll_h = nullptr, *mega_ll_qkv = nullptr, *mega_ll_act = nullptr, *mega_ll_pacc = nullptr,
+                       *mega_ll_pml = nullptr, *mega_ll_keys = nullptr;
+    uint32_t mega_seq = 0;                   // sequence numbers consumed by earlier launches
     int* mega_abort = nullptr;               // pinned host flag, device-visible
     unsigned long long* mega_prof = nullptr; // device [4][n_phases+1] phase timestamps (debug)
 

@@ -73,6 +73,10 @@ struct MegaArgs {
     int attn_tps;       // context tokens per attention split (work item)
     int max_inflight;   // bulk copies issued but not yet landed, per CTA (bounds queueing latency in L2/HBM)
     int l2_ahead;       // chunks prefetched into L2 beyond the ring (0 = off)
+    // dataflow mode (kernel template LL): activations travel as 8-byte {fp32 bits, sequence number} words and every
+    // reader polls for the sequence number of the phase that produces its input -- no grid barrier anywhere
+    unsigned long long *ll_h, *ll_qkv, *ll_act, *ll_pacc, *ll_pml, *ll_keys;
+    uint32_t seq_base;  // sequence numbers used by earlier launches
     unsigned long long* prof;  // optional [9][n_phases + 1], see b2l_debug_mega_profile globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
 };
 
@@ -187,6 +191,73 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 
 // rows [r0, r1) of an N-row matrix owned by CTA `c` of `G` (unit = 2 rows for SwiGLU pairs)
+// ---- dataflow words: {value, seq} in one 8-byte store; a 16-byte load brings two adjacent words ----
+__device__ __forceinline__ void ll_st(unsigned long long* p, float v, uint32_t seq) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((static_cast<unsigned long long>(seq) << 32) | __float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ uint4 ll_ld2(const unsigned long long* p) {  // .x/.z values, .y/.w sequence numbers
+    uint4 w;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p) : "memory");
+    return w;
+}
+// one lane per warp watches the first word pair of the warp's region until it carries `seq`: the whole grid polling
+// every word would cost terabytes per second of L2 traffic while the slowest producer finishes
+__device__ __forceinline__ void ll_sentinel(const unsigned long long* p, uint32_t seq, int lane, int* abort_flag, int code) {
+    if (lane == 0) {
+        unsigned spins = 0;
+        for (;;) {
+            const uint4 w = ll_ld2(p);
+            if (w.y == seq && w.w == seq) break;
+            if (++spins > (1u << 22)) mega_die(abort_flag, code);
+        }
+    }
+    __syncwarp();
+}
+// N x 8 consecutive words -> floats; retried (with a short back-off) until every word carries `seq`
+template <int N>
+__device__ __forceinline__ void ll_ld8n(const unsigned long long* const (&p)[N], uint32_t seq, float* out, int* abort_flag, int code) {
+    unsigned spins = 0;
+    for (;;) {
+        uint4 w[N][4];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) w[i][j] = ll_ld2(p[i] + 2 * j);
+        }
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ok = ok && w[i][j].y == seq && w[i][j].w == seq;
+        }
+        if (ok) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    out[i * 8 + 2 * j] = __uint_as_float(w[i][j].x);
+                    out[i * 8 + 2 * j + 1] = __uint_as_float(w[i][j].z);
+                }
+            }
+            return;
+        }
+        __nanosleep(64);
+        if (++spins > (1u << 22)) mega_die(abort_flag, code);
+    }
+}
+__device__ __forceinline__ void ll_ld4(const unsigned long long* p, uint32_t seq, float4& v, int* abort_flag, int code) {
+    unsigned spins = 0;
+    for (;;) {
+        const uint4 w0 = ll_ld2(p), w1 = ll_ld2(p + 2);
+        if (w0.y == seq && w0.w == seq && w1.y == seq && w1.w == seq) {
+            v = make_float4(__uint_as_float(w0.x), __uint_as_float(w0.z), __uint_as_float(w1.x), __uint_as_float(w1.z));
+            return;
+        }
+        __nanosleep(64);
+        if (++spins > (1u << 22)) mega_die(abort_flag, code);
+    }
+}
+
 __device__ __forceinline__ void mega_row_range(int N, int unit, int c, int G, int& r0, int& r1) {
     const long long units = N / unit;
     r0 = static_cast<int>(units * c / G) * unit;
@@ -334,6 +405,67 @@ __device__ __forceinline__ void mega_attn_combine8(const MegaArgs& /*unused: c_m
     for (int i = 0; i < 8; i++) out[i] = acc[i] * inv;
 }
 
+// dataflow variant: the partials are {value, seq} words written by the attention items of phase `seq`
+__device__ __forceinline__ void mega_attn_combine8_ll(int k, int nsplit, uint32_t seq, float* out) {
+    const MegaArgs& a = c_mega;
+    const int head = k / a.hd, d = k % a.hd;
+    const int group = a.nh / a.nkv, kvh = head / group, g = head % group;
+    const size_t rbase = static_cast<size_t>(kvh) * a.nsplit_max;
+    float Mx = -INFINITY, L = 0.f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+    for (int s0 = 0; s0 < nsplit; s0 += 2) {
+        float ml[2][2], pa[2][8];
+        unsigned spins = 0;
+        for (;;) {
+            uint4 wm[2], wa[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int sp = min(s0 + u, nsplit - 1);
+                const size_t rec = (rbase + sp) * group + g;
+                wm[u] = ll_ld2(a.ll_pml + rec * 2);
+#pragma unroll
+                for (int j = 0; j < 4; j++) wa[u][j] = ll_ld2(a.ll_pacc + rec * a.hd + d + 2 * j);
+            }
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                ok = ok && wm[u].y == seq && wm[u].w == seq;
+#pragma unroll
+                for (int j = 0; j < 4; j++) ok = ok && wa[u][j].y == seq && wa[u][j].w == seq;
+            }
+            if (ok) {
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    ml[u][0] = __uint_as_float(wm[u].x);
+                    ml[u][1] = __uint_as_float(wm[u].z);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        pa[u][2 * j] = __uint_as_float(wa[u][j].x);
+                        pa[u][2 * j + 1] = __uint_as_float(wa[u][j].z);
+                    }
+                }
+                break;
+            }
+            __nanosleep(64);
+            if (++spins > (1u << 22)) mega_die(a.abort_flag, 120);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (s0 + u >= nsplit || ml[u][0] == -INFINITY) continue;
+            const float mn = fmaxf(Mx, ml[u][0]);
+            const float c_old = __expf(Mx - mn), c_new = __expf(ml[u][0] - mn);
+            L = L * c_old + ml[u][1] * c_new;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = acc[i] * c_old + pa[u][i] * c_new;
+            Mx = mn;
+        }
+    }
+    const float inv = 1.0f / L;
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = acc[i] * inv;
+}
+
 // everything the consumer threads carry across phases, in registers
 struct ConsumerState {
     RingPos rp;
@@ -360,13 +492,48 @@ __device__ __forceinline__ void mega_phase_barrier(const MegaArgs& /*unused: c_m
     }
 }
 
+// token boundary in dataflow mode: every CTA published the best (logit, index) key of its lm_head rows as two
+// {32 bits, seq} words; all consumer threads of the CTA poll them and take the maximum
+__device__ __forceinline__ int mega_poll_token(const MegaSmem& sm, uint32_t want, int tid) {
+    const MegaArgs& a = c_mega;
+    const int lane = tid & 31, w = tid >> 5;
+    unsigned long long best = 0ull;
+    for (int c = tid; c < static_cast<int>(gridDim.x); c += kMegaConsumerThreads) {
+        unsigned spins = 0;
+        for (;;) {
+            const uint4 wk = ll_ld2(a.ll_keys + 2 * c);
+            if (wk.y == want && wk.w == want) {
+                const unsigned long long k = (static_cast<unsigned long long>(wk.x) << 32) | wk.z;
+                best = k > best ? k : best;
+                break;
+            }
+            __nanosleep(32);
+            if (++spins > (1u << 22)) mega_die(a.abort_flag, 130);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other > best ? other : best;
+    }
+    consumer_bar();   // sm.keys may still be read by a slow warp of the previous lm_head epilogue
+    if (lane == 0) sts64(sm.keys + w * 8, best);
+    consumer_bar();
+    best = lds64(sm.keys);
+    for (int i = 1; i < kMegaConsumerWarps; i++) {
+        const unsigned long long o = lds64(sm.keys + i * 8);
+        best = o > best ? o : best;
+    }
+    return argmax_key_index(best);
+}
+
 // ---- one GEMV-type phase for one CTA ---------------------------------------------------------
 #ifdef MEGA_GEMV_INLINE
 #define MEGA_GEMV_ATTR __forceinline__
 #else
 #define MEGA_GEMV_ATTR __noinline__
 #endif
-template <int M, bool SPLIT>  // SPLIT: K is split over ks > 1 warps
+template <int M, bool SPLIT, bool LL>  // SPLIT: K is split over ks > 1 warps; LL: dataflow words instead of grid barriers
 __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs ph, const MegaSmem sm, ConsumerState& st_ref,
                                              int pi, int pos, int tid) {
     const MegaArgs& a = c_mega;
@@ -392,7 +559,17 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         for (int i = 0; i < M; i++) nw[i] = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + q * slice + i * 256 + lane * 8));
     }
     const bool from_embed = (type == PH_QKV && ph.layer == 0);
-    mega_phase_barrier(a, st, from_embed && st.step > 0, tid);
+    const uint32_t gp = a.seq_base + static_cast<uint32_t>(st.step * a.n_phases + pi) + 1u;  // this phase's sequence number
+    const uint32_t want = gp - 1u;                                                           // inputs come from the phase before
+    if (LL) {
+        if (from_embed && st.step > 0) {
+            st.token = mega_poll_token(sm, want, tid);
+            if (blockIdx.x == 0 && tid == 0) a.out_ids[st.step - 1] = st.token;
+            __threadfence();  // order this step's KV-cache reads after everything the previous step published
+        }
+    } else {
+        mega_phase_barrier(a, st, from_embed && st.step > 0, tid);
+    }
     if (prof) prof_col[(prow + 1) * pstride] = globaltimer_ns();
     if (progress) *progress = st.step * 100000 + pi * 100 + 2;
 
@@ -403,10 +580,20 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
     float xr[M * 8];
     if (!SPLIT) {
         // every warp needs the same K floats: fetch once per CTA, then fan out through smem
+        if (LL && !from_embed) {
+            // wait (one lane per warp) for the first words of this warp's share, then fetch; stragglers are retried
+            if (type == PH_OPROJ) {
+                const int k0 = min((tid & ~31) * 8, K - 8), head = k0 / a.hd, group = a.nh / a.nkv;
+                ll_sentinel(a.ll_pml + ((static_cast<size_t>(head / group) * a.nsplit_max) * group + head % group) * 2, want, lane, a.abort_flag, 140);
+            } else {
+                ll_sentinel((type == PH_DOWN ? a.ll_act : a.ll_h) + min((tid & ~31) * 4, K - 4), want, lane, a.abort_flag, 141 + type);
+            }
+        }
         if (type == PH_OPROJ) {
             for (int k = tid * 8; k < K; k += kMegaConsumerThreads * 8) {
                 float v[8];
-                mega_attn_combine8(a, k, nsplit, v);
+                if (LL) mega_attn_combine8_ll(k, nsplit, want, v);
+                else mega_attn_combine8(a, k, nsplit, v);
                 sts128f(sm.xs + k * 4, make_float4(v[0], v[1], v[2], v[3]));
                 sts128f(sm.xs + k * 4 + 16, make_float4(v[4], v[5], v[6], v[7]));
             }
@@ -416,6 +603,8 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 if (from_embed) {
                     const uint2 e = __ldg(reinterpret_cast<const uint2*>(a.embed + static_cast<size_t>(token) * a.H + k));
                     v = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
+                } else if (LL) {
+                    ll_ld4((type == PH_DOWN ? a.ll_act : a.ll_h) + k, want, v, a.abort_flag, 150 + type);
                 } else {
                     v = __ldcg(reinterpret_cast<const float4*>(xsrc + k));
                 }
@@ -429,12 +618,29 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
             xr[i * 8 + 0] = v0.x; xr[i * 8 + 1] = v0.y; xr[i * 8 + 2] = v0.z; xr[i * 8 + 3] = v0.w;
             xr[i * 8 + 4] = v1.x; xr[i * 8 + 5] = v1.y; xr[i * 8 + 6] = v1.z; xr[i * 8 + 7] = v1.w;
         }
+    } else if (LL && !from_embed && type != PH_OPROJ) {
+        const unsigned long long* src = (type == PH_DOWN ? a.ll_act : a.ll_h) + q * slice + lane * 8;
+        ll_sentinel(src - lane * 8, want, lane, a.abort_flag, 160 + type);
+#pragma unroll
+        for (int i = 0; i + 1 < M; i += 2) {  // two 8-word groups (8 x 16-byte loads) in flight per lane
+            const unsigned long long* const pp[2] = {src + i * 256, src + (i + 1) * 256};
+            ll_ld8n<2>(pp, want, &xr[i * 8], a.abort_flag, 170 + type);
+        }
+        if (M & 1) {
+            const unsigned long long* const pp[1] = {src + (M - 1) * 256};
+            ll_ld8n<1>(pp, want, &xr[(M - 1) * 8], a.abort_flag, 170 + type);
+        }
     } else {
+        if (LL && type == PH_OPROJ) {
+            const int head = (q * slice) / a.hd, group = a.nh / a.nkv;
+            ll_sentinel(a.ll_pml + ((static_cast<size_t>(head / group) * a.nsplit_max) * group + head % group) * 2, want, lane, a.abort_flag, 140);
+        }
 #pragma unroll
         for (int i = 0; i < M; i++) {
             const int k = q * slice + i * 256 + lane * 8;
             if (type == PH_OPROJ) {
-                mega_attn_combine8(a, k, nsplit, &xr[i * 8]);
+                if (LL) mega_attn_combine8_ll(k, nsplit, want, &xr[i * 8]);
+                else mega_attn_combine8(a, k, nsplit, &xr[i * 8]);
                 continue;
             }
             float4 v0, v1;
@@ -504,7 +710,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         const bool row_live = live && row_t < r1;
         float resid = 0.f;  // residual input, fetched before the wait so its L2 latency overlaps
         if (out_lane && row_live && q == 0) {
-            if (resid_h) resid = __ldcg(a.h + row_t);
+            if (resid_h) resid = LL ? __ldcg(reinterpret_cast<const float*>(a.ll_h + row_t)) : __ldcg(a.h + row_t);
             else if (resid_e) resid = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row_t]);
         }
         float2 acc[kMegaRows];
@@ -607,15 +813,20 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         }
         if (out_lane && row_live) {
             if (type == PH_QKV) {
-                a.qkv[row_t] = s;
+                if (LL) ll_st(a.ll_qkv + row_t, s, gp);
+                else a.qkv[row_t] = s;
             } else if (type == PH_GATEUP) {
-                if ((my_t & 1) == 0) a.act[row_t >> 1] = s;
+                if ((my_t & 1) == 0) {
+                    if (LL) ll_st(a.ll_act + (row_t >> 1), s, gp);
+                    else a.act[row_t >> 1] = s;
+                }
             } else if (type == PH_LMHEAD) {
                 a.logits[row_t] = s;
                 const unsigned long long key = argmax_key(s, row_t);
                 best_key = key > best_key ? key : best_key;
             } else {
-                a.h[row_t] = resid + s;  // O-proj / down: residual add
+                if (LL) ll_st(a.ll_h + row_t, resid + s, gp);  // O-proj / down: residual add
+                else a.h[row_t] = resid + s;
             }
         }
     }
@@ -627,9 +838,9 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
 }
 
 // ---- attention work item: (kv head, split); partials are merged by the O-proj phase's x load -----
-template <int HD, int GROUP>
+template <int HD, int GROUP, bool LL>
 __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, uint32_t scratch, int kvh, int split, int nsplit,
-                                            int pos, int tid, unsigned long long* pcol, int group_total, int g0) {
+                                            int pos, int tid, unsigned long long* pcol, int group_total, int g0, uint32_t gp) {
     // processes query heads kvh*group_total + g0 .. + GROUP (GROUP == group_total, or 1 in per-query-head mode)
     const MegaArgs& a = c_mega;
     long long ak0 = 0, ak1 = 0, ak2 = 0, ak3 = 0, ak4 = 0, ak5 = 0;
@@ -643,13 +854,23 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
     const float* cs = a.rope + static_cast<size_t>(pos) * HD;  // [HALF][2]
     const int qd = a.nh * HD;
 
-    // rotate-half RoPE of one 8-wide slice of a head living in the fused qkv row
-    auto rope_slice = [&](const float* head, float* out) {
+    // rotate-half RoPE of one 8-wide slice of a head living in the fused qkv row (element offset `head`)
+    const uint32_t want = gp - 1u;
+    auto rope_slice = [&](int head, float* out) {
         const int d0 = sl * 8, j0r = d0 < HALF ? d0 : d0 - HALF;  // the slice lies in one half (HALF % 8 == 0)
-        const float4 xa0 = __ldcg(reinterpret_cast<const float4*>(head + j0r)), xa1 = __ldcg(reinterpret_cast<const float4*>(head + j0r + 4));
-        const float4 xb0 = __ldcg(reinterpret_cast<const float4*>(head + j0r + HALF)), xb1 = __ldcg(reinterpret_cast<const float4*>(head + j0r + HALF + 4));
-        const float x0[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
-        const float x1[8] = {xb0.x, xb0.y, xb0.z, xb0.w, xb1.x, xb1.y, xb1.z, xb1.w};
+        float xx[16];
+        if (LL) {
+            const unsigned long long* const pp[2] = {a.ll_qkv + head + j0r, a.ll_qkv + head + j0r + HALF};
+            ll_ld8n<2>(pp, want, xx, a.abort_flag, 180);
+        } else {
+            const float* hp = a.qkv + head;
+            const float4 xa0 = __ldcg(reinterpret_cast<const float4*>(hp + j0r)), xa1 = __ldcg(reinterpret_cast<const float4*>(hp + j0r + 4));
+            const float4 xb0 = __ldcg(reinterpret_cast<const float4*>(hp + j0r + HALF)), xb1 = __ldcg(reinterpret_cast<const float4*>(hp + j0r + HALF + 4));
+            xx[0] = xa0.x; xx[1] = xa0.y; xx[2] = xa0.z; xx[3] = xa0.w; xx[4] = xa1.x; xx[5] = xa1.y; xx[6] = xa1.z; xx[7] = xa1.w;
+            xx[8] = xb0.x; xx[9] = xb0.y; xx[10] = xb0.z; xx[11] = xb0.w; xx[12] = xb1.x; xx[13] = xb1.y; xx[14] = xb1.z; xx[15] = xb1.w;
+        }
+        const float* x0 = xx;
+        const float* x1 = xx + 8;
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
             const float4 c2 = __ldg(reinterpret_cast<const float4*>(cs + 2 * (j0r + i)));  // (c, s, c', s')
@@ -657,10 +878,11 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
             out[i + 1] = d0 < HALF ? x0[i + 1] * c2.z - x1[i + 1] * c2.w : x1[i + 1] * c2.z + x0[i + 1] * c2.w;
         }
     };
+    if (LL) ll_sentinel(a.ll_qkv + (kvh * group_total + g0) * HD, want, lane, a.abort_flag, 181);
     float q[GROUP][8];
 #pragma unroll
     for (int g = 0; g < GROUP; g++) {
-        rope_slice(a.qkv + (kvh * group_total + g0 + g) * HD, q[g]);
+        rope_slice((kvh * group_total + g0 + g) * HD, q[g]);
 #pragma unroll
         for (int i = 0; i < 8; i++) q[g][i] *= a.attn_scale;
     }
@@ -696,14 +918,25 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
                 if (j == pos) {
                     // the token being decoded: K/V come from this step's projection; append them (bf16)
                     float kr[8];
-                    rope_slice(a.qkv + qd + kvh * HD, kr);
-                    const float* vsrc = a.qkv + qd + a.kvd + kvh * HD + sl * 8;
-                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(vsrc)), v1 = __ldcg(reinterpret_cast<const float4*>(vsrc + 4));
+                    rope_slice(qd + kvh * HD, kr);
+                    float4 v0, v1;
+                    if (LL) {
+                        float vv[8];
+                        const unsigned long long* const pp[1] = {a.ll_qkv + qd + a.kvd + kvh * HD + sl * 8};
+                        ll_ld8n<1>(pp, want, vv, a.abort_flag, 182);
+                        v0 = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                        v1 = make_float4(vv[4], vv[5], vv[6], vv[7]);
+                    } else {
+                        const float* vsrc = a.qkv + qd + a.kvd + kvh * HD + sl * 8;
+                        v0 = __ldcg(reinterpret_cast<const float4*>(vsrc));
+                        v1 = __ldcg(reinterpret_cast<const float4*>(vsrc + 4));
+                    }
                     kw[u] = make_uint4(pack_bf16x2(kr[0], kr[1]), pack_bf16x2(kr[2], kr[3]), pack_bf16x2(kr[4], kr[5]), pack_bf16x2(kr[6], kr[7]));
                     vw[u] = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
                     if (g0 == 0) {  // one writer per kv head
                         *reinterpret_cast<uint4*>(kp) = kw[u];
                         *reinterpret_cast<uint4*>(vp) = vw[u];
+                        if (LL) __threadfence();  // the cache line must be out before this item's partials announce the phase done
                     }
                 } else {
                     kw[u] = __ldcg(reinterpret_cast<const uint4*>(kp));
@@ -783,10 +1016,18 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
                 A = fmaf(lds32f(s_acc + ((t * GROUP + g) * HD + d) * 4), wgt, A);
             }
         }
-        a.part_acc[(pbase * group_total + g0 + g) * HD + d] = A;
-        if (d == 0) {
-            a.part_ml[(pbase * group_total + g0 + g) * 2] = Mx;
-            a.part_ml[(pbase * group_total + g0 + g) * 2 + 1] = L;
+        if (LL) {
+            ll_st(a.ll_pacc + (pbase * group_total + g0 + g) * HD + d, A, gp);
+            if (d == 0) {
+                ll_st(a.ll_pml + (pbase * group_total + g0 + g) * 2, Mx, gp);
+                ll_st(a.ll_pml + (pbase * group_total + g0 + g) * 2 + 1, L, gp);
+            }
+        } else {
+            a.part_acc[(pbase * group_total + g0 + g) * HD + d] = A;
+            if (d == 0) {
+                a.part_ml[(pbase * group_total + g0 + g) * 2] = Mx;
+                a.part_ml[(pbase * group_total + g0 + g) * 2 + 1] = L;
+            }
         }
     }
     if (pcol) {
@@ -800,20 +1041,20 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
     }
 }
 
-template <int HD>
+template <int HD, bool LL>
 __device__ __forceinline__ void mega_attn_group(const MegaArgs& a, uint16_t* kv_pool, uint32_t scratch, int kvh, int split,
-                                                int nsplit, int pos, int tid, unsigned long long* pcol, int g_only) {
+                                                int nsplit, int pos, int tid, unsigned long long* pcol, int g_only, uint32_t gp) {
     const int group = a.nh / a.nkv;
     if (g_only >= 0) {
-        mega_attn_item<HD, 1>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, group, g_only);
+        mega_attn_item<HD, 1, LL>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, group, g_only, gp);
         return;
     }
     switch (group) {
-        case 1: mega_attn_item<HD, 1>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 1, 0); break;
-        case 2: mega_attn_item<HD, 2>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 2, 0); break;
-        case 3: mega_attn_item<HD, 3>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 3, 0); break;
-        case 4: mega_attn_item<HD, 4>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 4, 0); break;
-        default: mega_attn_item<HD, 8>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 8, 0); break;
+        case 1: mega_attn_item<HD, 1, LL>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 1, 0, gp); break;
+        case 2: mega_attn_item<HD, 2, LL>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 2, 0, gp); break;
+        case 3: mega_attn_item<HD, 3, LL>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 3, 0, gp); break;
+        case 4: mega_attn_item<HD, 4, LL>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 4, 0, gp); break;
+        default: mega_attn_item<HD, 8, LL>(a, kv_pool, scratch, kvh, split, nsplit, pos, tid, pcol, 8, 0, gp); break;
     }
 }
 
@@ -860,6 +1101,7 @@ struct ChunkCursor {
     }
 };
 
+template <bool LL>
 __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     const MegaArgs& a = c_mega;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -971,7 +1213,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                 const bool prof = a.prof && step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
                 const int prow = blockIdx.x == 0 ? 0 : 4, pstride = a.n_phases + 1;
                 if (prof) a.prof[(prow + 0) * pstride + pi] = globaltimer_ns();
-                mega_phase_barrier(a, st, false, tid);
+                if (!LL) mega_phase_barrier(a, st, false, tid);
+                const uint32_t gp = a.seq_base + static_cast<uint32_t>(step * a.n_phases + pi) + 1u;
                 if (prof) a.prof[(prow + 1) * pstride + pi] = a.prof[(prow + 2) * pstride + pi] = globaltimer_ns();
                 const AttnPlan plan = mega_attn_plan(a.nsplit_max, pos + 1, a.attn_tps, a.nh, gridDim.x);
                 const int nsplit = plan.nsplit, item = blockIdx.x;
@@ -982,37 +1225,37 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                     const int kvh = plan.per_q_head ? unit / group : unit;
                     const int g_only = plan.per_q_head ? unit % group : -1;
                     unsigned long long* pcol = prof && blockIdx.x == 0 ? a.prof + pi : nullptr;
-                    if (a.hd == 64) mega_attn_group<64>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only);
-                    else if (a.hd == 128) mega_attn_group<128>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only);
-                    else mega_attn_group<32>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only);
+                    if (a.hd == 64) mega_attn_group<64, LL>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only, gp);
+                    else if (a.hd == 128) mega_attn_group<128, LL>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only, gp);
+                    else mega_attn_group<32, LL>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only, gp);
                 }
                 if (prof) a.prof[(prow + 3) * pstride + pi] = globaltimer_ns();
             } else {
 #ifdef MEGA_ONLY_1B
-                if (ph.ks == 1) mega_gemv_phase<8, false>(a, ph, sm, st, pi, pos, tid);
-                else mega_gemv_phase<8, true>(a, ph, sm, st, pi, pos, tid);
+                if (ph.ks == 1) mega_gemv_phase<8, false, LL>(a, ph, sm, st, pi, pos, tid);
+                else mega_gemv_phase<8, true, LL>(a, ph, sm, st, pi, pos, tid);
 #else
                 if (ph.ks == 1) {
                     switch (ph.m) {
-                        case 1: mega_gemv_phase<1, false>(a, ph, sm, st, pi, pos, tid); break;
-                        case 2: mega_gemv_phase<2, false>(a, ph, sm, st, pi, pos, tid); break;
-                        case 3: mega_gemv_phase<3, false>(a, ph, sm, st, pi, pos, tid); break;
-                        case 4: mega_gemv_phase<4, false>(a, ph, sm, st, pi, pos, tid); break;
-                        case 5: mega_gemv_phase<5, false>(a, ph, sm, st, pi, pos, tid); break;
-                        case 6: mega_gemv_phase<6, false>(a, ph, sm, st, pi, pos, tid); break;
-                        case 7: mega_gemv_phase<7, false>(a, ph, sm, st, pi, pos, tid); break;
-                        default: mega_gemv_phase<8, false>(a, ph, sm, st, pi, pos, tid); break;
+                        case 1: mega_gemv_phase<1, false, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 2: mega_gemv_phase<2, false, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 3: mega_gemv_phase<3, false, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 4: mega_gemv_phase<4, false, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 5: mega_gemv_phase<5, false, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 6: mega_gemv_phase<6, false, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 7: mega_gemv_phase<7, false, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        default: mega_gemv_phase<8, false, LL>(a, ph, sm, st, pi, pos, tid); break;
                     }
                 } else {
                     switch (ph.m) {
-                        case 1: mega_gemv_phase<1, true>(a, ph, sm, st, pi, pos, tid); break;
-                        case 2: mega_gemv_phase<2, true>(a, ph, sm, st, pi, pos, tid); break;
-                        case 3: mega_gemv_phase<3, true>(a, ph, sm, st, pi, pos, tid); break;
-                        case 4: mega_gemv_phase<4, true>(a, ph, sm, st, pi, pos, tid); break;
-                        case 5: mega_gemv_phase<5, true>(a, ph, sm, st, pi, pos, tid); break;
-                        case 6: mega_gemv_phase<6, true>(a, ph, sm, st, pi, pos, tid); break;
-                        case 7: mega_gemv_phase<7, true>(a, ph, sm, st, pi, pos, tid); break;
-                        default: mega_gemv_phase<8, true>(a, ph, sm, st, pi, pos, tid); break;
+                        case 1: mega_gemv_phase<1, true, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 2: mega_gemv_phase<2, true, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 3: mega_gemv_phase<3, true, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 4: mega_gemv_phase<4, true, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 5: mega_gemv_phase<5, true, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 6: mega_gemv_phase<6, true, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        case 7: mega_gemv_phase<7, true, LL>(a, ph, sm, st, pi, pos, tid); break;
+                        default: mega_gemv_phase<8, true, LL>(a, ph, sm, st, pi, pos, tid); break;
                     }
                 }
 #endif
@@ -1034,12 +1277,30 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                         const unsigned long long o = lds64(sm.keys + i * 8);
                         k = o > k ? o : k;
                     }
-                    atomicMax(a.argmax_keys + (step % 3), k);
+                    if (LL) {
+                        const uint32_t gp = a.seq_base + static_cast<uint32_t>(step * a.n_phases + pi) + 1u;
+                        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(a.ll_keys + 2 * blockIdx.x),
+                                     "l"((static_cast<unsigned long long>(gp) << 32) | (k >> 32)),
+                                     "l"((static_cast<unsigned long long>(gp) << 32) | (k & 0xffffffffull)) : "memory");
+                    } else {
+                        atomicMax(a.argmax_keys + (step % 3), k);
+                    }
                 }
             }
             // the key two steps ahead was last read at the start of the previous step: safe to clear now
-            if (pi == 2 && blockIdx.x == 0 && tid == 0) a.argmax_keys[(step + 1) % 3] = 0ull;
+            if (!LL && pi == 2 && blockIdx.x == 0 && tid == 0) a.argmax_keys[(step + 1) % 3] = 0ull;
         }
+    }
+    if (LL) {
+        // only CTA 0 needs the last token: it waits for every CTA's key of the last lm_head phase
+        if (blockIdx.x != 0) return;
+        const int token = mega_poll_token(sm, a.seq_base + static_cast<uint32_t>(a.n_steps * a.n_phases), tid);
+        if (tid == 0) {
+            a.out_ids[a.n_steps - 1] = token;
+            *a.token = token;
+            *a.position = pos0 + a.n_steps;
+        }
+        return;
     }
     // final barrier: every CTA's lm_head rows are in the last key
     st.nbar++;
