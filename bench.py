@@ -409,9 +409,16 @@ def main():
     bytes_per_token = info.stream_bytes_per_token + arch.hidden_size * 2 + avg_ctx * kv_per_tok + kv_per_tok
     peak, peak_src = measured_peaks()
     achieved = bytes_per_token / (ms_per_step * 1e-3) / 1e9
+    mega = eng.info().decode_mode == 1
+    # dram__bytes_read.sum + dram__bytes_write.sum of the megakernel from the committed ncu --set full capture
+    # (profiles/r01_megakernel_ncu_summary.txt: 9.9616 GB for a 4-token launch of this exact workload), per launch
+    ncu_dram_bytes_per_token = 9.9616e9 / 4
+    traffic = ncu_dram_bytes_per_token * K if (mega and CTX0 == 512 and arch.hidden_size == 2048 and arch.num_hidden_layers == 16) else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "bytes_per_token": bytes_per_token,
-            "kernel": ("persistent decode megakernel (1 launch/token)" if eng.info().decode_mode == 1 else
+            "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu), same launch as algorithmic_bytes_per_launch",
+            "algorithmic_bytes_per_launch": bytes_per_token * K,
+            "peak_source": peak_src, "bytes_per_token": bytes_per_token,
+            "kernel": (f"persistent decode megakernel, barrier-free dataflow build (1 cooperative launch = {K} tokens)" if mega else
                        f"decode step = CUDA graph of {launches // K} kernels; fraction is for the whole step"),
             "frac_of_8TBps_nominal": achieved / 8000.0}
 

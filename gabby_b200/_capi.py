@@ -9,6 +9,7 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libb2l.so")
+LIB_PATH = os.environ.get("B2L_LIB_PATH", LIB_PATH)   # development builds (profiling variants); the default is the in-tree library
 
 # every symbol include/b2l.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [

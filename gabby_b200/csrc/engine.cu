@@ -738,6 +738,7 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     a.ll_h = c->mega_ll_h; a.ll_qkv = c->mega_ll_qkv; a.ll_act = c->mega_ll_act; a.ll_pacc = c->mega_ll_pacc;
     a.ll_pml = c->mega_ll_pml; a.ll_keys = c->mega_ll_keys;
     a.seq_base = c->mega_seq;
+    a.ll_use_sentinel = std::getenv("B2L_MEGA_SENTINEL") ? std::atoi(std::getenv("B2L_MEGA_SENTINEL")) : 0;
     if (c->mega_ll) c->mega_seq += static_cast<uint32_t>(n_steps) * static_cast<uint32_t>(c->mega_n_phases);
     int* dev_abort = nullptr;
     B2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_abort), c->mega_abort, 0));

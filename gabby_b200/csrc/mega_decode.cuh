@@ -77,6 +77,7 @@ struct MegaArgs {
     // reader polls for the sequence number of the phase that produces its input -- no grid barrier anywhere
     unsigned long long *ll_h, *ll_qkv, *ll_act, *ll_pacc, *ll_pml, *ll_keys;
     uint32_t seq_base;  // sequence numbers used by earlier launches
+    int ll_use_sentinel;  // 1: one lane per warp polls first, then everybody loads; 0: everybody polls its own words
     unsigned long long* prof;  // optional [9][n_phases + 1], see b2l_debug_mega_profile globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
 };
 
@@ -203,6 +204,7 @@ __device__ __forceinline__ uint4 ll_ld2(const unsigned long long* p) {  // .x/.z
 // one lane per warp watches the first word pair of the warp's region until it carries `seq`: the whole grid polling
 // every word would cost terabytes per second of L2 traffic while the slowest producer finishes
 __device__ __forceinline__ void ll_sentinel(const unsigned long long* p, uint32_t seq, int lane, int* abort_flag, int code) {
+    if (!c_mega.ll_use_sentinel) return;
     if (lane == 0) {
         unsigned spins = 0;
         for (;;) {
@@ -406,6 +408,7 @@ __device__ __forceinline__ void mega_attn_combine8(const MegaArgs& /*unused: c_m
 }
 
 // dataflow variant: the partials are {value, seq} words written by the attention items of phase `seq`
+template <int NB>  // splits fetched per round trip
 __device__ __forceinline__ void mega_attn_combine8_ll(int k, int nsplit, uint32_t seq, float* out) {
     const MegaArgs& a = c_mega;
     const int head = k / a.hd, d = k % a.hd;
@@ -414,13 +417,13 @@ __device__ __forceinline__ void mega_attn_combine8_ll(int k, int nsplit, uint32_
     float Mx = -INFINITY, L = 0.f, acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.f;
-    for (int s0 = 0; s0 < nsplit; s0 += 2) {
-        float ml[2][2], pa[2][8];
+    for (int s0 = 0; s0 < nsplit; s0 += NB) {
+        float ml[NB][2], pa[NB][8];
         unsigned spins = 0;
         for (;;) {
-            uint4 wm[2], wa[2][4];
+            uint4 wm[NB], wa[NB][4];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < NB; u++) {
                 const int sp = min(s0 + u, nsplit - 1);
                 const size_t rec = (rbase + sp) * group + g;
                 wm[u] = ll_ld2(a.ll_pml + rec * 2);
@@ -429,14 +432,14 @@ __device__ __forceinline__ void mega_attn_combine8_ll(int k, int nsplit, uint32_
             }
             bool ok = true;
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
+            for (int u = 0; u < NB; u++) {
                 ok = ok && wm[u].y == seq && wm[u].w == seq;
 #pragma unroll
                 for (int j = 0; j < 4; j++) ok = ok && wa[u][j].y == seq && wa[u][j].w == seq;
             }
             if (ok) {
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
+                for (int u = 0; u < NB; u++) {
                     ml[u][0] = __uint_as_float(wm[u].x);
                     ml[u][1] = __uint_as_float(wm[u].z);
 #pragma unroll
@@ -451,7 +454,7 @@ __device__ __forceinline__ void mega_attn_combine8_ll(int k, int nsplit, uint32_
             if (++spins > (1u << 22)) mega_die(a.abort_flag, 120);
         }
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < NB; u++) {
             if (s0 + u >= nsplit || ml[u][0] == -INFINITY) continue;
             const float mn = fmaxf(Mx, ml[u][0]);
             const float c_old = __expf(Mx - mn), c_new = __expf(ml[u][0] - mn);
@@ -592,7 +595,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         if (type == PH_OPROJ) {
             for (int k = tid * 8; k < K; k += kMegaConsumerThreads * 8) {
                 float v[8];
-                if (LL) mega_attn_combine8_ll(k, nsplit, want, v);
+                if (LL) mega_attn_combine8_ll<4>(k, nsplit, want, v);
                 else mega_attn_combine8(a, k, nsplit, v);
                 sts128f(sm.xs + k * 4, make_float4(v[0], v[1], v[2], v[3]));
                 sts128f(sm.xs + k * 4 + 16, make_float4(v[4], v[5], v[6], v[7]));
@@ -639,7 +642,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         for (int i = 0; i < M; i++) {
             const int k = q * slice + i * 256 + lane * 8;
             if (type == PH_OPROJ) {
-                if (LL) mega_attn_combine8_ll(k, nsplit, want, &xr[i * 8]);
+                if (LL) mega_attn_combine8_ll<2>(k, nsplit, want, &xr[i * 8]);
                 else mega_attn_combine8(a, k, nsplit, &xr[i * 8]);
                 continue;
             }
@@ -702,7 +705,13 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
     // this warp's first item: row group rloc -> stage index rloc * ks
     RingPos sp0 = rp0.plus(rloc * ks, n_stages);
     const int stage_step = groups_per_round * ks;       // = kMegaConsumerWarps stages per round
+#ifdef MEGA_PROF_ROUNDS
+    long long pr_wait = 0, pr_math = 0, pr_tail = 0, pr_t0 = 0, pr_t1 = 0, pr_t2 = 0;
+#endif
     for (int rd = 0; rd < n_rounds; rd++) {
+#ifdef MEGA_PROF_ROUNDS
+        pr_t0 = clock64();
+#endif
         const int rg = rd * groups_per_round + rloc;    // this warp's row group
         const int row0 = r0 + rg * kMegaRows;
         const bool live = rg < n_groups;
@@ -749,6 +758,9 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                     }
                 }
             }
+#ifdef MEGA_PROF_ROUNDS
+            pr_t1 = clock64();
+#endif
             uint4 wv[2][kMegaRows];
 #pragma unroll
             for (int t = 0; t < kMegaRows; t++) wv[0][t] = lds128(row_addr[t]);
@@ -787,6 +799,10 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 }
             }
         }
+#ifdef MEGA_PROF_ROUNDS
+        pr_t2 = clock64();
+        if (live) { pr_wait += pr_t1 - pr_t0; pr_math += pr_t2 - pr_t1; }
+#endif
         sp0 = sp0.plus(stage_step, n_stages);
         // transposed butterfly: 6 shuffles reduce all four rows; lane 8*t ends up with row t's sum.
         // Rows past the end of the range read a duplicate row; their sums are never stored.
@@ -829,7 +845,18 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 else a.h[row_t] = resid + s;
             }
         }
+#ifdef MEGA_PROF_ROUNDS
+        pr_tail += clock64() - pr_t2;
+#endif
     }
+#ifdef MEGA_PROF_ROUNDS
+    if (prof && blockIdx.x == 0) {
+        prof_col[9 * pstride] = pr_wait;
+        prof_col[10 * pstride] = pr_math;
+        prof_col[11 * pstride] = pr_tail;
+        prof_col[12 * pstride] = n_rounds;
+    }
+#endif
     st.rp = rp0.plus(n_stage_total, n_stages);
     st.best_key = best_key;
     st_ref = st;
@@ -878,6 +905,30 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
             out[i + 1] = d0 < HALF ? x0[i + 1] * c2.z - x1[i + 1] * c2.w : x1[i + 1] * c2.z + x0[i + 1] * c2.w;
         }
     };
+    constexpr int U = 4;  // token slots per lane group in flight: all K/V loads of a block are issued before any math
+    constexpr int STEP = U * kMegaConsumerWarps * TPW;
+    uint4 kw[U], vw[U];
+    // cached tokens do not depend on this step's projections: their K/V loads go out BEFORE the wait for q
+    auto load_block = [&](int jb) {
+        int page[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
+            page[u] = j < j1 ? __ldg(a.block_table + j / a.page_size) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
+            kw[u] = make_uint4(0, 0, 0, 0);
+            vw[u] = make_uint4(0, 0, 0, 0);
+            if (j < j1 && j != pos) {
+                const int off = j % a.page_size;
+                kw[u] = __ldcg(reinterpret_cast<const uint4*>(kv.at(page[u], 0, off) + kvh * HD + sl * 8));
+                vw[u] = __ldcg(reinterpret_cast<const uint4*>(kv.at(page[u], 1, off) + kvh * HD + sl * 8));
+            }
+        }
+    };
+    load_block(j0);
     if (LL) ll_sentinel(a.ll_qkv + (kvh * group_total + g0) * HD, want, lane, a.abort_flag, 181);
     float q[GROUP][8];
 #pragma unroll
@@ -895,52 +946,36 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
     }
-    constexpr int U = 4;  // token slots per lane group in flight: all K/V loads of a block are issued before any math
-    for (int jb = j0; jb < j1; jb += U * kMegaConsumerWarps * TPW) {
-        uint4 kw[U], vw[U];
+    for (int jb = j0; jb < j1; jb += STEP) {
+        if (jb != j0) load_block(jb);
         bool valid[U];
-        int page[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
             valid[u] = j < j1;
-            page[u] = valid[u] ? __ldg(a.block_table + j / a.page_size) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
-            kw[u] = make_uint4(0, 0, 0, 0);
-            vw[u] = make_uint4(0, 0, 0, 0);
-            if (valid[u]) {
-                const int off = j % a.page_size;
-                uint16_t* kp = kv.at(page[u], 0, off) + kvh * HD + sl * 8;
-                uint16_t* vp = kv.at(page[u], 1, off) + kvh * HD + sl * 8;
-                if (j == pos) {
-                    // the token being decoded: K/V come from this step's projection; append them (bf16)
-                    float kr[8];
-                    rope_slice(qd + kvh * HD, kr);
-                    float4 v0, v1;
-                    if (LL) {
-                        float vv[8];
-                        const unsigned long long* const pp[1] = {a.ll_qkv + qd + a.kvd + kvh * HD + sl * 8};
-                        ll_ld8n<1>(pp, want, vv, a.abort_flag, 182);
-                        v0 = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                        v1 = make_float4(vv[4], vv[5], vv[6], vv[7]);
-                    } else {
-                        const float* vsrc = a.qkv + qd + a.kvd + kvh * HD + sl * 8;
-                        v0 = __ldcg(reinterpret_cast<const float4*>(vsrc));
-                        v1 = __ldcg(reinterpret_cast<const float4*>(vsrc + 4));
-                    }
-                    kw[u] = make_uint4(pack_bf16x2(kr[0], kr[1]), pack_bf16x2(kr[2], kr[3]), pack_bf16x2(kr[4], kr[5]), pack_bf16x2(kr[6], kr[7]));
-                    vw[u] = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
-                    if (g0 == 0) {  // one writer per kv head
-                        *reinterpret_cast<uint4*>(kp) = kw[u];
-                        *reinterpret_cast<uint4*>(vp) = vw[u];
-                        if (LL) __threadfence();  // the cache line must be out before this item's partials announce the phase done
-                    }
+            if (valid[u] && j == pos) {
+                // the token being decoded: K/V come from this step's projection; append them (bf16)
+                float kr[8];
+                rope_slice(qd + kvh * HD, kr);
+                float4 v0, v1;
+                if (LL) {
+                    float vv[8];
+                    const unsigned long long* const pp[1] = {a.ll_qkv + qd + a.kvd + kvh * HD + sl * 8};
+                    ll_ld8n<1>(pp, want, vv, a.abort_flag, 182);
+                    v0 = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    v1 = make_float4(vv[4], vv[5], vv[6], vv[7]);
                 } else {
-                    kw[u] = __ldcg(reinterpret_cast<const uint4*>(kp));
-                    vw[u] = __ldcg(reinterpret_cast<const uint4*>(vp));
+                    const float* vsrc = a.qkv + qd + a.kvd + kvh * HD + sl * 8;
+                    v0 = __ldcg(reinterpret_cast<const float4*>(vsrc));
+                    v1 = __ldcg(reinterpret_cast<const float4*>(vsrc + 4));
+                }
+                kw[u] = make_uint4(pack_bf16x2(kr[0], kr[1]), pack_bf16x2(kr[2], kr[3]), pack_bf16x2(kr[4], kr[5]), pack_bf16x2(kr[6], kr[7]));
+                vw[u] = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+                if (g0 == 0) {  // one writer per kv head
+                    const int page = __ldg(a.block_table + j / a.page_size), off = j % a.page_size;
+                    *reinterpret_cast<uint4*>(kv.at(page, 0, off) + kvh * HD + sl * 8) = kw[u];
+                    *reinterpret_cast<uint4*>(kv.at(page, 1, off) + kvh * HD + sl * 8) = vw[u];
+                    if (LL) __threadfence();  // the cache line must be out before this item's partials announce the phase done
                 }
             }
         }

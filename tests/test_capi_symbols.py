@@ -35,7 +35,8 @@ def test_header_symbols_all_exported(lib):
 def test_struct_layouts_match_header():
     # b2l_params: 8 int32 + float + 8 int32; b2l_info ends with char[64]
     assert C.sizeof(_capi.B2lParams) == 17 * 4
-    assert C.sizeof(_capi.B2lInfo) == 4 * 4 + 5 * 8 + 8 + 64
+    # 4 int32 + 5 int64 + 3 int32 (decode_mode, batched_tensor_core, tp_transport) + char[64], padded to 8
+    assert C.sizeof(_capi.B2lInfo) == (4 * 4 + 5 * 8 + 3 * 4 + 64 + 7) // 8 * 8
 
 
 def test_no_cpu_fallback(lib):

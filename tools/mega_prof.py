@@ -29,6 +29,21 @@ for k in range(6):
           f"  (weight-wait {ns[8][sel].mean()/1.965e3:6.2f}) | ctaL: barrier {avg(ns[5]-ns[4]):6.2f}  xload {avg(ns[6]-ns[5]):6.2f}  rows {avg(ns[7]-ns[6]):7.2f}"
           f" | total {((ns[3]-ns[0])[sel].sum())/1e3:8.1f} us")
 
+# hand-off: end of the previous phase's rows (later of the two sampled CTAs) -> input vector ready in this phase
+prev_end = np.maximum(ns[3], ns[7])
+for k in range(6):
+    idx = np.nonzero(types == k)[0]
+    idx = idx[idx > 0]
+    if len(idx) == 0:
+        continue
+    h0 = (ns[2][idx] - prev_end[idx - 1]) / 1e3
+    hL = (ns[6][idx] - prev_end[idx - 1]) / 1e3
+    print(f"handoff into {names[k]:7s}: cta0 {h0.mean():6.2f} us   ctaL {hL.mean():6.2f} us   (previous phase end spread |cta0-ctaL| {np.abs(ns[3][idx-1]-ns[7][idx-1]).mean()/1e3:5.2f} us)")
+
+for k in (0, 2, 3, 4, 5):
+    sel = types == k
+    if sel.any() and ns[12][sel].mean() > 0:
+        print(f"{names[k]:7s} rounds {ns[12][sel].mean():4.1f}: per phase (us) stage-wait {ns[9][sel].mean()/1.965e3:6.2f}  lds+fma {ns[10][sel].mean()/1.965e3:6.2f}  butterfly+epilogue {ns[11][sel].mean()/1.965e3:6.2f}")
 sel = types == 1
 print("attention item breakdown, cta0 tid0 (us): q-rope / loads+scores / sub-slot merge / smem+barrier / CTA merge+store")
 print(" ".join(f"{ns[r][sel].mean()/1.965e3:6.2f}" for r in (9, 10, 11, 12, 13)))
