@@ -273,7 +273,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
     const int grp = warp * TPW + sub;
 
     const int ctx = a.rm.positions[r] + 1;
-    const int chunk = (ctx + nsplit - 1) / nsplit;
+    // the grid is sized for long contexts (several CTAs per SM); a short context uses only the first
+    // ceil(ctx / 64) splits, the other CTAs leave at once and are not counted by the merge
+    const int eff = max(1, min(nsplit, (ctx + 63) >> 6));
+    if (split >= eff) return;
+    const int chunk = (ctx + eff - 1) / eff;
     const int j0 = split * chunk, j1 = min(ctx, j0 + chunk);
     const int32_t* bt = a.rm.block_tables + static_cast<size_t>(a.rm.slots[r]) * a.rm.max_blocks;
 
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
     __syncthreads();
     if (tid == 0) {
         const int done = atomicAdd(a.counters + r * nkv + kvh, 1);
-        s_last = (done == nsplit - 1);
+        s_last = (done == eff - 1);
         if (s_last) a.counters[r * nkv + kvh] = 0;
     }
     __syncthreads();
@@ -381,9 +385,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
     for (int e = tid; e < GROUP * HD; e += kAttnThreads) {
         const int g = e / HD, d = e % HD;
         float M = -INFINITY;
-        for (int s = 0; s < nsplit; s++) M = fmaxf(M, __ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2));
+        for (int s = 0; s < eff; s++) M = fmaxf(M, __ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2));
         float L = 0.f, A = 0.f;
-        for (int s = 0; s < nsplit; s++) {
+        for (int s = 0; s < eff; s++) {
             const float ms = __ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2);
             if (ms == -INFINITY) continue;
             const float w = __expf(ms - M);

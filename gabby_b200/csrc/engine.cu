@@ -236,7 +236,13 @@ void gemv(b2l_ctx* c, const uint16_t* W, const float* x, int ldx, float* y, int 
 
 template <int HD>
 void attn_launch_hd(b2l_ctx* c, const AttnArgs& a, int R) {
-    const dim3 grid(c->nsplit, c->nkv_l, R), block(kAttnThreads);
+    // about four 128-thread CTAs per SM when the context is long (measured in one run, 3B batch 8, context 2048:
+    // 8 splits 3.67 ms/step, 16: 4.00, 32: 4.54 -- the last-arriver merge grows with the split count); the kernel
+    // trims the split count for short contexts
+    // (8B, 1 row, context 4096: 16 splits 5.36 ms/token, 32: 5.07, 64: 5.41)
+    const int want = std::min(32, (3 * c->prop.multiProcessorCount + c->nkv_l * R - 1) / (c->nkv_l * R));
+    static const int forced = std::getenv("B2L_ATTN_SPLITS") ? std::atoi(std::getenv("B2L_ATTN_SPLITS")) : 0;   // tuning knob
+    const dim3 grid(std::max(1, std::min(c->nsplit, forced > 0 ? forced : want)), c->nkv_l, R), block(kAttnThreads);
     switch (c->group) {
         case 1: launch(c, attn_decode_kernel<HD, 1>, grid, block, 0, a); break;
         case 2: launch(c, attn_decode_kernel<HD, 2>, grid, block, 0, a); break;
@@ -476,8 +482,10 @@ void prefill_alloc(b2l_ctx* c) {
     c->pf_act16 = dalloc<uint16_t>(c, T * c->I_l);
     if (c->p.tp_size > 1) c->pf_proj = dalloc<float>(c, T * H);
     const size_t rows = kPfAttnChunk;
-    c->pf_part_acc = dalloc<float>(c, rows * c->nkv_l * c->nsplit * c->group * c->hd);
-    c->pf_part_ml = dalloc<float>(c, rows * c->nkv_l * c->nsplit * c->group * 2);
+    // rows x splits of one launch never exceeds rows + 8 SMs / kv heads (attn_launch_hd sizes the split count by the rows)
+    const size_t row_splits = rows + static_cast<size_t>(8 * c->prop.multiProcessorCount) / c->nkv_l + 1;
+    c->pf_part_acc = dalloc<float>(c, row_splits * c->nkv_l * c->group * c->hd);
+    c->pf_part_ml = dalloc<float>(c, row_splits * c->nkv_l * c->group * 2);
     c->pf_counters = dalloc<int>(c, rows * c->nkv_l);
     c->pf_tiles = dalloc<PrefillTile>(c, T / 1 + static_cast<size_t>(c->p.max_batch));  // <= one tile per row in the worst case
     B2L_CUDA(cudaMemset(c->pf_counters, 0, sizeof(int) * rows * c->nkv_l));
@@ -658,7 +666,7 @@ void mega_setup(b2l_ctx* c) {
     if (c->nkv_l > G) return no("more kv heads than SMs");
     c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
     const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
-    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 64 + 128 + 4 * 2 * kMegaConsumerWarps * kMegaRows + sizeof(float) * kMegaXsFloats + 48 * ph.size() + attn_scratch + 256;
+    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 64 + 128 + 4 * 2 * kMegaConsumerWarps * kMegaRows + sizeof(float) * kMegaXsFloats + 2 * static_cast<size_t>(c->H) + 48 * ph.size() + attn_scratch + 256;
     int max_smem = 0;
     B2L_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->p.device));
     const int stages = std::min<int>(kMegaMaxStages, static_cast<int>((static_cast<size_t>(max_smem) - fixed) / kMegaStageBytes));
@@ -952,8 +960,7 @@ int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_
         c->group = p->num_heads / p->num_kv_heads;
         c->max_rows = (std::max(p->max_batch, 8) + 7) / 8 * 8;
         c->max_blocks_cap = (p->max_positions + p->page_size - 1) / p->page_size;
-        c->nsplit = std::max(1, std::min(32, (c->prop.multiProcessorCount + c->nkv_l - 1) / c->nkv_l));
-        if (c->nsplit > 16 && c->nkv_l >= 8) c->nsplit = 16;
+        c->nsplit = std::max(1, std::min(64, (8 * c->prop.multiProcessorCount + c->nkv_l - 1) / c->nkv_l));   // capacity of the split-K partial buffers
 
         // weights
         const size_t H = c->H;

@@ -286,6 +286,7 @@ struct MegaSmem {
     uint32_t ring;          // [n_stages][kMegaStageBytes]
     uint32_t full, empty;   // [n_stages] mbarriers each
     uint32_t xs;            // [kMegaXsFloats] fp32
+    uint32_t nw;            // [H] bf16: the phase's RMSNorm weight (cp.async before the input poll)
     uint32_t red;           // [32] fp32
     uint32_t part;          // [2][8] fp32 per-chunk partial sums (double buffered)
     uint32_t keys;          // [8] u64
@@ -556,10 +557,11 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
     // ---- static prologue: nothing here depends on other CTAs, so it overlaps the barrier wait ----
     int r0, r1;
     mega_row_range(ph.N, type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
-    uint4 nw[M];
     if (ph.norm_w) {
-#pragma unroll
-        for (int i = 0; i < M; i++) nw[i] = __ldg(reinterpret_cast<const uint4*>(ph.norm_w + q * slice + i * 256 + lane * 8));
+        // RMSNorm weight -> shared memory, asynchronously (no registers held across the input poll, no scoreboard wait)
+        for (int k = tid * 8; k < K; k += kMegaConsumerThreads * 8)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sm.nw + k * 2), "l"(ph.norm_w + k) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     const bool from_embed = (type == PH_QKV && ph.layer == 0);
     const uint32_t gp = a.seq_base + static_cast<uint32_t>(st.step * a.n_phases + pi) + 1u;  // this phase's sequence number
@@ -614,6 +616,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 sts128f(sm.xs + k * 4, v);
             }
         }
+        if (ph.norm_w) asm volatile("cp.async.wait_group 0;" ::: "memory");
         consumer_bar();
 #pragma unroll
         for (int i = 0; i < M; i++) {
@@ -624,14 +627,22 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
     } else if (LL && !from_embed && type != PH_OPROJ) {
         const unsigned long long* src = (type == PH_DOWN ? a.ll_act : a.ll_h) + q * slice + lane * 8;
         ll_sentinel(src - lane * 8, want, lane, a.abort_flag, 160 + type);
+        if (M == 8) {  // four 8-word groups (16 x 16-byte loads) in flight per lane: two round trips for the slice
 #pragma unroll
-        for (int i = 0; i + 1 < M; i += 2) {  // two 8-word groups (8 x 16-byte loads) in flight per lane
-            const unsigned long long* const pp[2] = {src + i * 256, src + (i + 1) * 256};
-            ll_ld8n<2>(pp, want, &xr[i * 8], a.abort_flag, 170 + type);
-        }
-        if (M & 1) {
-            const unsigned long long* const pp[1] = {src + (M - 1) * 256};
-            ll_ld8n<1>(pp, want, &xr[(M - 1) * 8], a.abort_flag, 170 + type);
+            for (int i = 0; i < 8; i += 4) {
+                const unsigned long long* const pp[4] = {src + i * 256, src + (i + 1) * 256, src + (i + 2) * 256, src + (i + 3) * 256};
+                ll_ld8n<4>(pp, want, &xr[i * 8], a.abort_flag, 170 + type);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i + 1 < M; i += 2) {
+                const unsigned long long* const pp[2] = {src + i * 256, src + (i + 1) * 256};
+                ll_ld8n<2>(pp, want, &xr[i * 8], a.abort_flag, 170 + type);
+            }
+            if (M & 1) {
+                const unsigned long long* const pp[1] = {src + (M - 1) * 256};
+                ll_ld8n<1>(pp, want, &xr[(M - 1) * 8], a.abort_flag, 170 + type);
+            }
         }
     } else {
         if (LL && type == PH_OPROJ) {
@@ -666,6 +677,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         float ss = warp_sum((ssq[0] + ssq[1]) + (ssq[2] + ssq[3]));
         if (SPLIT) {  // a warp holds only its K slice: add the other slices' sums (warps 0..ks-1)
             if (lane == 0) sts32f(sm.red + w * 4, ss);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             consumer_bar();
             ss = 0.f;
             for (int i = 0; i < ks; i++) ss += lds32f(sm.red + i * 4);
@@ -673,14 +685,15 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         const float inv = rsqrtf(ss / static_cast<float>(K) + a.eps);
 #pragma unroll
         for (int i = 0; i < M; i++) {
-            xr[i * 8 + 0] = bf16lo(nw[i].x) * (xr[i * 8 + 0] * inv);
-            xr[i * 8 + 1] = bf16hi(nw[i].x) * (xr[i * 8 + 1] * inv);
-            xr[i * 8 + 2] = bf16lo(nw[i].y) * (xr[i * 8 + 2] * inv);
-            xr[i * 8 + 3] = bf16hi(nw[i].y) * (xr[i * 8 + 3] * inv);
-            xr[i * 8 + 4] = bf16lo(nw[i].z) * (xr[i * 8 + 4] * inv);
-            xr[i * 8 + 5] = bf16hi(nw[i].z) * (xr[i * 8 + 5] * inv);
-            xr[i * 8 + 6] = bf16lo(nw[i].w) * (xr[i * 8 + 6] * inv);
-            xr[i * 8 + 7] = bf16hi(nw[i].w) * (xr[i * 8 + 7] * inv);
+            const uint4 nwi = lds128(sm.nw + (q * slice + i * 256 + lane * 8) * 2);
+            xr[i * 8 + 0] = bf16lo(nwi.x) * (xr[i * 8 + 0] * inv);
+            xr[i * 8 + 1] = bf16hi(nwi.x) * (xr[i * 8 + 1] * inv);
+            xr[i * 8 + 2] = bf16lo(nwi.y) * (xr[i * 8 + 2] * inv);
+            xr[i * 8 + 3] = bf16hi(nwi.y) * (xr[i * 8 + 3] * inv);
+            xr[i * 8 + 4] = bf16lo(nwi.z) * (xr[i * 8 + 4] * inv);
+            xr[i * 8 + 5] = bf16hi(nwi.z) * (xr[i * 8 + 5] * inv);
+            xr[i * 8 + 6] = bf16lo(nwi.w) * (xr[i * 8 + 6] * inv);
+            xr[i * 8 + 7] = bf16hi(nwi.w) * (xr[i * 8 + 7] * inv);
         }
     }
     if (prof) prof_col[(prow + 2) * pstride] = globaltimer_ns();
@@ -1150,6 +1163,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     sm.red = p;   p += 4 * 32;
     sm.part = p;  p += 4 * 2 * kMegaConsumerWarps * kMegaRows;
     sm.xs = p;    p += 4 * kMegaXsFloats;
+    sm.nw = p;    p += 2 * static_cast<uint32_t>(a.H);
     sm.phases = p; p += 48 * static_cast<uint32_t>(a.n_phases);
     sm.attn_scratch = p;
 
