@@ -190,10 +190,11 @@ class Engine:
         return i
 
     def mega_profile(self, enable=True):
-        """-> (ns [9][n_phases+1] uint64, phase_types [n_phases]) of the last megakernel token"""
+        """-> (ns [16 + 2*160][n_phases+1] uint64, phase_types [n_phases]) of the last megakernel token: rows 0-15 summary
+        (CTA 0 / last CTA), rows 16.. input-ready time per CTA, rows 176.. phase-end time per CTA"""
         n = C.c_int(0)
         self._ck(self.L.b2l_debug_mega_profile(self.h, int(enable), None, C.byref(n), None), "mega_profile")
-        ns = np.zeros((16, n.value + 1), dtype=np.uint64)
+        ns = np.zeros((16 + 2 * 160, n.value + 1), dtype=np.uint64)   # kMegaProfRows
         types = np.zeros(n.value, dtype=np.int32)
         self._ck(self.L.b2l_debug_mega_profile(self.h, int(enable), _p(ns), C.byref(n), _p(types)), "mega_profile")
         return ns, types

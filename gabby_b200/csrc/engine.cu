@@ -1398,7 +1398,7 @@ int b2l_debug_mega_profile(b2l_ctx* c, int enable, uint64_t* out_ns, int* n_phas
     return guarded(c, [&] {
         require_ready(c);
         B2L_CHECK(c->mega_ok, "megakernel unavailable: " + c->mega_why);
-        const size_t n = 16 * static_cast<size_t>(c->mega_n_phases + 1);
+        const size_t n = static_cast<size_t>(kMegaProfRows) * static_cast<size_t>(c->mega_n_phases + 1);
         if (enable && !c->mega_prof) {
             c->mega_prof = dalloc<unsigned long long>(c, n);
             B2L_CUDA(cudaMemset(c->mega_prof, 0, n * 8));

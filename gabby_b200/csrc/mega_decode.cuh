@@ -27,6 +27,7 @@ constexpr int kMegaStageBytes = 16 * 1024;
 constexpr int kMegaMaxStages = 12;
 constexpr int kMegaRows = 4;  // rows one warp reduces together (transposed butterfly)
 constexpr int kMegaXsFloats = 2048;
+constexpr int kMegaProfRows = 16 + 2 * 160;  // debug timeline: 16 summary rows, then per CTA: input-ready and phase-end times
 
 enum MegaPhaseType { PH_QKV = 0, PH_ATTN = 1, PH_OPROJ = 2, PH_GATEUP = 3, PH_DOWN = 4, PH_LMHEAD = 5 };
 
@@ -216,15 +217,21 @@ __device__ __forceinline__ void ll_sentinel(const unsigned long long* p, uint32_
     __syncwarp();
 }
 // N x 8 consecutive words -> floats; retried (with a short back-off) until every word carries `seq`
+// Position of element k inside the h / act word vectors: within each 256-element block the four word PAIRS a lane
+// owns (k = blk*256 + lane*8 + e) are spread 64 words apart, so that a warp's 16-byte load number j covers 512
+// contiguous bytes (fully coalesced) instead of 32 scattered 64-byte chunks.
+__device__ __forceinline__ int ll_perm(int k) { return (k & ~255) | (((k >> 1) & 3) << 6) | (((k >> 3) & 31) << 1) | (k & 1); }
+
 template <int N>
-__device__ __forceinline__ void ll_ld8n(const unsigned long long* const (&p)[N], uint32_t seq, float* out, int* abort_flag, int code) {
+__device__ __forceinline__ void ll_ld8n(const unsigned long long* const (&p)[N], uint32_t seq, float* out, int* abort_flag, int code,
+                                        int pair_stride = 2) {
     unsigned spins = 0;
     for (;;) {
         uint4 w[N][4];
 #pragma unroll
         for (int i = 0; i < N; i++) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) w[i][j] = ll_ld2(p[i] + 2 * j);
+            for (int j = 0; j < 4; j++) w[i][j] = ll_ld2(p[i] + pair_stride * j);
         }
         bool ok = true;
 #pragma unroll
@@ -602,14 +609,36 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 sts128f(sm.xs + k * 4, make_float4(v[0], v[1], v[2], v[3]));
                 sts128f(sm.xs + k * 4 + 16, make_float4(v[4], v[5], v[6], v[7]));
             }
+        } else if (LL && !from_embed) {
+            // a warp fetches 256 consecutive words with four fully coalesced 16-byte loads per lane (512 contiguous
+            // bytes per instruction), all in flight: one round trip for K <= 2048
+            const unsigned long long* src = (type == PH_DOWN ? a.ll_act : a.ll_h);
+            for (int k0 = w * 256; k0 < K; k0 += kMegaConsumerWarps * 256) {
+                unsigned spins = 0;
+                for (;;) {
+                    uint4 wd[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) wd[j] = ll_ld2(src + k0 + j * 64 + lane * 2);
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) ok = ok && wd[j].y == want && wd[j].w == want;
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(sm.xs + (k0 + lane * 8 + 2 * j) * 4), "f"(__uint_as_float(wd[j].x)),
+                                         "f"(__uint_as_float(wd[j].z)) : "memory");
+                        break;
+                    }
+                    __nanosleep(64);
+                    if (++spins > (1u << 22)) mega_die(a.abort_flag, 150 + type);
+                }
+            }
         } else {
             for (int k = tid * 4; k < K; k += kMegaConsumerThreads * 4) {
                 float4 v;
                 if (from_embed) {
                     const uint2 e = __ldg(reinterpret_cast<const uint2*>(a.embed + static_cast<size_t>(token) * a.H + k));
                     v = make_float4(bf16lo(e.x), bf16hi(e.x), bf16lo(e.y), bf16hi(e.y));
-                } else if (LL) {
-                    ll_ld4((type == PH_DOWN ? a.ll_act : a.ll_h) + k, want, v, a.abort_flag, 150 + type);
                 } else {
                     v = __ldcg(reinterpret_cast<const float4*>(xsrc + k));
                 }
@@ -625,23 +654,23 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
             xr[i * 8 + 4] = v1.x; xr[i * 8 + 5] = v1.y; xr[i * 8 + 6] = v1.z; xr[i * 8 + 7] = v1.w;
         }
     } else if (LL && !from_embed && type != PH_OPROJ) {
-        const unsigned long long* src = (type == PH_DOWN ? a.ll_act : a.ll_h) + q * slice + lane * 8;
-        ll_sentinel(src - lane * 8, want, lane, a.abort_flag, 160 + type);
+        const unsigned long long* src = (type == PH_DOWN ? a.ll_act : a.ll_h) + q * slice + lane * 2;   // permuted layout: see ll_perm
+        ll_sentinel(src - lane * 2, want, lane, a.abort_flag, 160 + type);
         if (M == 8) {  // four 8-word groups (16 x 16-byte loads) in flight per lane: two round trips for the slice
 #pragma unroll
             for (int i = 0; i < 8; i += 4) {
                 const unsigned long long* const pp[4] = {src + i * 256, src + (i + 1) * 256, src + (i + 2) * 256, src + (i + 3) * 256};
-                ll_ld8n<4>(pp, want, &xr[i * 8], a.abort_flag, 170 + type);
+                ll_ld8n<4>(pp, want, &xr[i * 8], a.abort_flag, 170 + type, 64);
             }
         } else {
 #pragma unroll
             for (int i = 0; i + 1 < M; i += 2) {
                 const unsigned long long* const pp[2] = {src + i * 256, src + (i + 1) * 256};
-                ll_ld8n<2>(pp, want, &xr[i * 8], a.abort_flag, 170 + type);
+                ll_ld8n<2>(pp, want, &xr[i * 8], a.abort_flag, 170 + type, 64);
             }
             if (M & 1) {
                 const unsigned long long* const pp[1] = {src + (M - 1) * 256};
-                ll_ld8n<1>(pp, want, &xr[(M - 1) * 8], a.abort_flag, 170 + type);
+                ll_ld8n<1>(pp, want, &xr[(M - 1) * 8], a.abort_flag, 170 + type, 64);
             }
         }
     } else {
@@ -697,6 +726,8 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         }
     }
     if (prof) prof_col[(prow + 2) * pstride] = globaltimer_ns();
+    const bool prof_all = a.prof && st.step == a.n_steps - 1 && tid == 0 && blockIdx.x < 160;
+    if (prof_all) prof_col[(16 + blockIdx.x) * pstride] = globaltimer_ns();
     if (progress) *progress = st.step * 100000 + pi * 100 + 3;
 
     // ---- stream this CTA's rows: a warp takes kMegaRows rows (x its K slice) at a time ----
@@ -732,7 +763,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         const bool row_live = live && row_t < r1;
         float resid = 0.f;  // residual input, fetched before the wait so its L2 latency overlaps
         if (out_lane && row_live && q == 0) {
-            if (resid_h) resid = LL ? __ldcg(reinterpret_cast<const float*>(a.ll_h + row_t)) : __ldcg(a.h + row_t);
+            if (resid_h) resid = LL ? __ldcg(reinterpret_cast<const float*>(a.ll_h + ll_perm(row_t))) : __ldcg(a.h + row_t);
             else if (resid_e) resid = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row_t]);
         }
         float2 acc[kMegaRows];
@@ -846,7 +877,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 else a.qkv[row_t] = s;
             } else if (type == PH_GATEUP) {
                 if ((my_t & 1) == 0) {
-                    if (LL) ll_st(a.ll_act + (row_t >> 1), s, gp);
+                    if (LL) ll_st(a.ll_act + ll_perm(row_t >> 1), s, gp);
                     else a.act[row_t >> 1] = s;
                 }
             } else if (type == PH_LMHEAD) {
@@ -854,7 +885,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 const unsigned long long key = argmax_key(s, row_t);
                 best_key = key > best_key ? key : best_key;
             } else {
-                if (LL) ll_st(a.ll_h + row_t, resid + s, gp);  // O-proj / down: residual add
+                if (LL) ll_st(a.ll_h + ll_perm(row_t), resid + s, gp);  // O-proj / down: residual add
                 else a.h[row_t] = resid + s;
             }
         }
@@ -875,6 +906,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
     st_ref = st;
     if (progress) *progress = st.step * 100000 + pi * 100 + 4;
     if (prof) prof_col[(prow + 3) * pstride] = globaltimer_ns();
+    if (prof_all) prof_col[(16 + 160 + blockIdx.x) * pstride] = globaltimer_ns();
 }
 
 // ---- attention work item: (kv head, split); partials are merged by the O-proj phase's x load -----
@@ -1279,6 +1311,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                     else mega_attn_group<32, LL>(a, ph.kv_pool, sm.attn_scratch, kvh, split, nsplit, pos, tid, pcol, g_only, gp);
                 }
                 if (prof) a.prof[(prow + 3) * pstride + pi] = globaltimer_ns();
+                if (a.prof && step == a.n_steps - 1 && tid == 0 && blockIdx.x < 160)
+                    a.prof[(16 + 160 + blockIdx.x) * pstride + pi] = item < n_items ? globaltimer_ns() : 0ull;
             } else {
 #ifdef MEGA_ONLY_1B
                 if (ph.ks == 1) mega_gemv_phase<8, false, LL>(a, ph, sm, st, pi, pos, tid);

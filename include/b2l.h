@@ -136,7 +136,7 @@ int b2l_set_decode_mode(b2l_ctx* c, int mode);
 int b2l_set_prefill_mode(b2l_ctx* c, int mode);
 
 /* Debug: per-phase device timestamps (globaltimer ns) of the last token of the last megakernel
- * launch. enable=1 arms it; out_ns (optional) is [9][n_phases+1], column = phase: rows 0-3 CTA 0
+ * launch. enable=1 arms it; out_ns (optional) is [336][n_phases+1], column = phase: rows 0-3 CTA 0
  * {phase entry, dependency barrier passed, input vector loaded, phase end}, rows 4-7 the same for
  * the last CTA, row 8 CTA 0 warp 0 cycles spent waiting for weights.
  * phase_types (optional) [n_phases]: 0 qkv 1 attn 2 o 3 gate/up 4 down 5 lm_head. */

@@ -40,6 +40,29 @@ for k in range(6):
     hL = (ns[6][idx] - prev_end[idx - 1]) / 1e3
     print(f"handoff into {names[k]:7s}: cta0 {h0.mean():6.2f} us   ctaL {hL.mean():6.2f} us   (previous phase end spread |cta0-ctaL| {np.abs(ns[3][idx-1]-ns[7][idx-1]).mean()/1e3:5.2f} us)")
 
+# all CTAs: when did each one have its input / finish its rows, relative to the first CTA to finish the phase before
+G = 148
+ready = ns[16:16 + G, :n]
+end = ns[176:176 + G, :n]
+for k in range(6):
+    idx = np.nonzero(types == k)[0]
+    idx = idx[idx > 1]
+    if len(idx) == 0:
+        continue
+    rows = []
+    for i in idx:
+        e_prev = end[:, i - 1][end[:, i - 1] > 0]
+        if k == 1:
+            e_this = end[:, i][end[:, i] > 0]
+            rows.append((0, 0, 0, (e_this.max() - e_this.min()) / 1e3, (e_this.max() - e_prev.max()) / 1e3))
+            continue
+        r = ready[:, i][ready[:, i] > 0]
+        e_this = end[:, i][end[:, i] > 0]
+        rows.append(((e_prev.max() - e_prev.min()) / 1e3, (r.min() - e_prev.max()) / 1e3, (r.max() - e_prev.max()) / 1e3,
+                     (e_this.max() - e_this.min()) / 1e3, (e_this.max() - e_prev.max()) / 1e3))
+    m = np.array(rows).mean(axis=0)
+    print(f"all CTAs, {names[k]:7s}: prev-phase end spread {m[0]:5.2f} | input ready after last prev end: first CTA {m[1]:5.2f}, last CTA {m[2]:5.2f} | this-phase end spread {m[3]:5.2f} | phase length (last end -> last end) {m[4]:6.2f} us")
+
 for k in (0, 2, 3, 4, 5):
     sel = types == k
     if sel.any() and ns[12][sel].mean() > 0:
