@@ -695,10 +695,10 @@ void mega_setup(b2l_ctx* c) {
             B2L_CUDA(cudaMemset(p, 0, words * sizeof(unsigned long long)));
             return p;
         };
-        c->mega_ll_h = zalloc(c->H);
+        c->mega_ll_h = zalloc((static_cast<size_t>(c->H) + 255) / 256 * 256);
         c->mega_ll_qkv = zalloc(c->qkv_l);
-        c->mega_ll_act = zalloc(c->I_l);
-        c->mega_ll_pacc = zalloc(n_part * c->hd);
+        c->mega_ll_act = zalloc((static_cast<size_t>(c->I_l) + 255) / 256 * 256);
+        c->mega_ll_pacc = zalloc((n_part * c->hd + 255) / 256 * 256);   // ll_perm permutes within 256-word blocks
         c->mega_ll_pml = zalloc(n_part * 2);
         c->mega_ll_keys = zalloc(static_cast<size_t>(2) * G);
         c->mega_seq = 0;

@@ -436,7 +436,9 @@ __device__ __forceinline__ void mega_attn_combine8_ll(int k, int nsplit, uint32_
                 const size_t rec = (rbase + sp) * group + g;
                 wm[u] = ll_ld2(a.ll_pml + rec * 2);
 #pragma unroll
-                for (int j = 0; j < 4; j++) wa[u][j] = ll_ld2(a.ll_pacc + rec * a.hd + d + 2 * j);
+                const unsigned long long* pa0 = a.ll_pacc + ll_perm(static_cast<int>(rec) * a.hd + d);   // d % 8 == 0: pairs 64 words apart
+#pragma unroll
+                for (int j = 0; j < 4; j++) wa[u][j] = ll_ld2(pa0 + 64 * j);
             }
             bool ok = true;
 #pragma unroll
@@ -1097,7 +1099,7 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
             }
         }
         if (LL) {
-            ll_st(a.ll_pacc + (pbase * group_total + g0 + g) * HD + d, A, gp);
+            ll_st(a.ll_pacc + ll_perm(static_cast<int>((pbase * group_total + g0 + g) * HD + d)), A, gp);
             if (d == 0) {
                 ll_st(a.ll_pml + (pbase * group_total + g0 + g) * 2, Mx, gp);
                 ll_st(a.ll_pml + (pbase * group_total + g0 + g) * 2 + 1, L, gp);
