@@ -105,6 +105,12 @@ def cpu_decode_sample(arch, n_prefill: int, n_steps: int, warm: int):
     """Oracle (port) decode tok/s on the host cores. Returns (tok/s, cores, description)."""
     from gabby_b200 import synth
     from oracle import pyoracle as po
+    # torchrun exports OMP_NUM_THREADS=1; the CPU leg is meant to use every host core this process may run on
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count() or 1
+    po.lib().orc_set_num_threads(usable)
     tensors = {n: synth.gen_tensor_bits(n, int(np.prod(s)), sc, off, SEED) for n, s, sc, off in synth.tensor_specs(arch)}
     om = po.OracleModel(arch, tensors, n_prefill + warm + n_steps + 1)
     s = om.seq(po.ORC_KV_BF16)

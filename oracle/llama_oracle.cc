@@ -134,6 +134,9 @@ void orc_synth_tensor(uint32_t tensor_seed, int64_t n, float scale, float offset
 }
 
 int orc_num_threads(void) { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}
 
 orc_model* orc_model_create(const orc_params* p) {
     if (p->head_dim % 8 || p->hidden_size % 8 || p->intermediate_size % 8) return nullptr;

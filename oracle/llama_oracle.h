@@ -99,6 +99,8 @@ void orc_rope_inv_freq(const orc_params* p, float* out);
 void orc_synth_tensor(uint32_t tensor_seed, int64_t n, float scale, float offset, uint16_t* out_bits);
 
 int orc_num_threads(void);
+/* launchers such as torchrun export OMP_NUM_THREADS=1: the timed CPU legs set the thread count explicitly */
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -63,6 +63,7 @@ def _bind(lib):
     lib.orc_rope_inv_freq.argtypes = [C.POINTER(OrcParams), vp]
     lib.orc_synth_tensor.argtypes = [C.c_uint32, C.c_int64, C.c_float, C.c_float, vp]
     lib.orc_num_threads.restype = C.c_int
+    lib.orc_set_num_threads.argtypes = [C.c_int]
     return lib
 
 
