@@ -270,47 +270,54 @@ void tap_copy(b2l_ctx* c, int slab, int row0, const float* src, int R) {
 CUtensorMap make_kmajor_map(const uint16_t* ptr, int64_t rows, int64_t cols, int box_rows);  // defined below
 
 // ---- batched decode (2..16 rows) on the tensor cores -----------------------------------------------
-constexpr size_t kSkinnySmem = static_cast<size_t>(kSkinnyStages) * (128 * kGemmBK * 2 + 4096) + 16 * kSkinnyStages + 64 + 1024;
-
 void skinny_setup(b2l_ctx* c) {
     c->skinny_ok = false;
-    const bool shapes = c->qkv_l % 128 == 0 && c->H % 128 == 0 && (2 * c->I_l) % 128 == 0 && c->V_l % 128 == 0 &&
-                        c->H % 64 == 0 && c->qd_l % 64 == 0 && c->I_l % 64 == 0 && c->p.max_batch >= 2;
+    // K must be a whole number of 64-element TMA boxes; N only has to be even (TMA zero-fills the rows past N)
+    const bool shapes = c->H % 64 == 0 && c->qd_l % 64 == 0 && c->I_l % 64 == 0 && c->qkv_l % 2 == 0 && c->V_l % 2 == 0 &&
+                        c->qkv_l >= 128 && c->H >= 128 && c->p.max_batch >= 2;
     if (!shapes) return;
-    c->sk_xh = dalloc<uint16_t>(c, static_cast<size_t>(32) * c->H);
-    c->sk_xq = dalloc<uint16_t>(c, static_cast<size_t>(32) * c->qd_l);
-    c->sk_xi = dalloc<uint16_t>(c, static_cast<size_t>(32) * c->I_l);
-    B2L_CUDA(cudaMemset(c->sk_xh, 0, sizeof(uint16_t) * 32 * c->H));
-    B2L_CUDA(cudaMemset(c->sk_xq, 0, sizeof(uint16_t) * 32 * c->qd_l));
-    B2L_CUDA(cudaMemset(c->sk_xi, 0, sizeof(uint16_t) * 32 * c->I_l));
+    c->sk_xh = dalloc<uint16_t>(c, static_cast<size_t>(64) * c->H);
+    c->sk_xq = dalloc<uint16_t>(c, static_cast<size_t>(64) * c->qd_l);
+    c->sk_xi = dalloc<uint16_t>(c, static_cast<size_t>(64) * c->I_l);
+    B2L_CUDA(cudaMemset(c->sk_xh, 0, sizeof(uint16_t) * 64 * c->H));
+    B2L_CUDA(cudaMemset(c->sk_xq, 0, sizeof(uint16_t) * 64 * c->qd_l));
+    B2L_CUDA(cudaMemset(c->sk_xi, 0, sizeof(uint16_t) * 64 * c->I_l));
     const size_t max_n = std::max<size_t>(static_cast<size_t>(c->V_l), static_cast<size_t>(2) * c->I_l);
-    c->sk_partial_floats = std::max<size_t>(max_n * 16, static_cast<size_t>(32) * 16 * 8192);
+    c->sk_partial_floats = std::max<size_t>(max_n * 32, static_cast<size_t>(32) * 32 * 8192);
     c->sk_partial = dalloc<float>(c, c->sk_partial_floats);
-    B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSkinnySmem)));
-    B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSkinnySmem)));
+    B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(skinny_smem(16))));
+    B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(skinny_smem(32))));
+    B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(skinny_smem(64))));
     c->skinny_ok = true;
 }
 
-// y (op)= W x for R (2..16) activation rows: prep (hi/lo bf16 [+ RMSNorm]) -> tcgen05 skinny GEMM -> split reduce + epilogue
+// y (op)= W x for R >= 2 activation rows, 32 rows per pass: prep (hi/lo bf16 [+ RMSNorm]) -> tcgen05 skinny GEMM -> split
+// reduce + epilogue
 void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, int ldx, const uint16_t* norm_w, uint16_t* xbuf,
-                   float* y, int ldy, int mode, int R, const TpSend* tps = nullptr) {
-    const int BT = R <= 8 ? 16 : 32, T = BT / 2;
-    if (norm_w) launch(c, split_bf16_kernel<true>, dim3(R), dim3(256), 0, x, ldx, norm_w, xbuf, K, T, c->p.rms_norm_eps);
-    else launch(c, split_bf16_kernel<false>, dim3(R), dim3(256), 0, x, ldx, static_cast<const uint16_t*>(nullptr), xbuf, K, T, 0.f);
-    const int n_tiles = N / 128, n_kblocks = K / kGemmBK;
-    // two CTAs per SM are resident: size the K split so the grid is (at most) one full wave
-    int ksplit = std::max(1, std::min({2 * c->prop.multiProcessorCount / n_tiles, n_kblocks / 2, 32}));
-    while (static_cast<size_t>(ksplit) * T * N > c->sk_partial_floats && ksplit > 1) ksplit--;
-    const int per_split = (n_kblocks + ksplit - 1) / ksplit;
-    ksplit = (n_kblocks + per_split - 1) / per_split;
-    const CUtensorMap mw = make_kmajor_map(W, N, K, 128), mx = make_kmajor_map(xbuf, BT, K, BT);
-    const dim3 grid(n_tiles, ksplit);
-    const size_t smem = kSkinnySmem;
-    if (BT == 16) launch(c, skinny_gemm_kernel<16>, grid, dim3(kSkinnyThreads), smem, mw, mx, c->sk_partial, N, n_kblocks, per_split);
-    else launch(c, skinny_gemm_kernel<32>, grid, dim3(kSkinnyThreads), smem, mw, mx, c->sk_partial, N, n_kblocks, per_split);
-    const int cols = mode == 2 ? N / 2 : N;
-    launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, y, ldy,
-           tps ? *tps : TpSend{});
+                   float* y, int ldy, int mode, int R_all, const TpSend* tps = nullptr) {
+    for (int r0 = 0; r0 < R_all; r0 += 32) {
+        const int R = std::min(32, R_all - r0);
+        const float* xg = x + static_cast<size_t>(r0) * ldx;
+        float* yg = y ? y + static_cast<size_t>(r0) * ldy : nullptr;
+        const int BT = R <= 8 ? 16 : R <= 16 ? 32 : 64, T = BT / 2;
+        if (norm_w) launch(c, split_bf16_kernel<true>, dim3(R), dim3(256), 0, xg, ldx, norm_w, xbuf, K, T, c->p.rms_norm_eps);
+        else launch(c, split_bf16_kernel<false>, dim3(R), dim3(256), 0, xg, ldx, static_cast<const uint16_t*>(nullptr), xbuf, K, T, 0.f);
+        const int n_tiles = (N + 127) / 128, n_kblocks = K / kGemmBK;
+        // two CTAs per SM are resident: size the K split so the grid is (at most) one full wave
+        int ksplit = std::max(1, std::min({2 * c->prop.multiProcessorCount / n_tiles, n_kblocks / 2, 32}));
+        while (static_cast<size_t>(ksplit) * T * N > c->sk_partial_floats && ksplit > 1) ksplit--;
+        const int per_split = (n_kblocks + ksplit - 1) / ksplit;
+        ksplit = (n_kblocks + per_split - 1) / per_split;
+        const CUtensorMap mw = make_kmajor_map(W, N, K, 128), mx = make_kmajor_map(xbuf, BT, K, BT);
+        const dim3 grid(n_tiles, ksplit);
+        if (BT == 16) launch(c, skinny_gemm_kernel<16>, grid, dim3(kSkinnyThreads), skinny_smem(16), mw, mx, c->sk_partial, N, n_kblocks, per_split);
+        else if (BT == 32) launch(c, skinny_gemm_kernel<32>, grid, dim3(kSkinnyThreads), skinny_smem(32), mw, mx, c->sk_partial, N, n_kblocks, per_split);
+        else launch(c, skinny_gemm_kernel<64>, grid, dim3(kSkinnyThreads), skinny_smem(64), mw, mx, c->sk_partial, N, n_kblocks, per_split);
+        const int cols = mode == 2 ? N / 2 : N;
+        TpSend send = tps ? *tps : TpSend{};
+        for (int p = 0; p < send.tp; p++) send.dst[p] += static_cast<size_t>(r0) * ldy;
+        launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, yg, ldy, send);
+    }
 }
 
 // ---- TP over peer memory: the projection kernel's epilogue stores its partial sums into every rank's slab,
@@ -429,7 +436,7 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
     for (int l = 0; l < c->L; l++) {
         const LayerWeights& w = c->layers[l];
         const KvLayout kv{w.kv_pool, c->p.page_size, c->kvd_l};
-        const bool sk = c->skinny_ok && R >= 2 && R <= 16;   // batched decode: projections on the tensor cores
+        const bool sk = c->skinny_ok && R >= 2;   // batched decode: projections on the tensor cores
         if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R);
         else gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
         launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
@@ -458,7 +465,7 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         c->launched++;
     }
     if (want_logits) {
-        if (c->skinny_ok && R >= 2 && R <= 16) skinny_linear(c, c->lm_head, c->V_l, c->H, c->h, c->H, c->final_norm, c->sk_xh, c->logits, c->V_l, 0, R);
+        if (c->skinny_ok && R >= 2) skinny_linear(c, c->lm_head, c->V_l, c->H, c->h, c->H, c->final_norm, c->sk_xh, c->logits, c->V_l, 0, R);
         else gemv(c, c->lm_head, c->h, c->H, c->logits, c->V_l, c->final_norm, c->V_l, c->H, 0, R);
         tp_argmax(c, c->logits, R);
     }

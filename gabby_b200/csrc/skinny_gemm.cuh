@@ -14,15 +14,19 @@
 
 namespace b2l {
 
-constexpr int kSkinnyStages = 5, kSkinnyThreads = 192;   // 5 x 20 KB: two CTAs per SM, the whole grid is one wave
+constexpr int kSkinnyThreads = 192;
+// ring depth and stage size per activation-tile width BT: two CTAs per SM stay resident (the whole grid is one wave)
+__host__ __device__ constexpr int skinny_stages(int BT) { return BT <= 32 ? 5 : 4; }
+__host__ __device__ constexpr uint32_t skinny_stage_bytes(int BT) { return 128 * kGemmBK * 2 + (BT * kGemmBK * 2 < 4096 ? 4096 : BT * kGemmBK * 2); }
+__host__ __device__ constexpr size_t skinny_smem(int BT) { return static_cast<size_t>(skinny_stages(BT)) * skinny_stage_bytes(BT) + 16 * skinny_stages(BT) + 64 + 1024; }
 
-template <int BT>  // columns of the MMA: 2 x (max rows), 16 or 32
+template <int BT>  // columns of the MMA: 2 x (max rows): 16, 32 or 64
 __global__ void __launch_bounds__(kSkinnyThreads, 2)
 skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ partial,
                    int N, int n_kblocks, int kblocks_per_split) {
-    constexpr uint32_t kStageW = 128 * kGemmBK * 2, kStageX = BT * kGemmBK * 2;   // x tile padded to 4 KB (keeps 1024-byte alignment)
-    static_assert(kStageX <= 4096, "x tile");
-    constexpr uint32_t kStageBytes = kStageW + 4096;
+    constexpr uint32_t kStageW = 128 * kGemmBK * 2, kStageX = BT * kGemmBK * 2;   // x tile padded to >= 4 KB (keeps 1024-byte alignment)
+    constexpr uint32_t kStageBytes = skinny_stage_bytes(BT);
+    constexpr int kSkinnyStages = skinny_stages(BT);
     extern __shared__ __align__(1024) uint8_t ssm[];
     const uint32_t base = (smem_u32(ssm) + 1023u) & ~1023u;
     const uint32_t bars = base + kSkinnyStages * kStageBytes;
@@ -41,7 +45,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(32) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BT < 32 ? 32 : BT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
@@ -108,7 +112,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BT < 32 ? 32 : BT) : "memory");
     }
 }
 

@@ -186,7 +186,7 @@ def test_batched_decode_ragged_lengths_matches_per_sequence_oracle():
         assert ids[:, i].tolist() == oids[1:].tolist(), (i, float(margins.min()))
 
 
-@pytest.mark.parametrize("n_seq", [5, 12])
+@pytest.mark.parametrize("n_seq", [5, 12, 20])
 def test_batched_decode_on_tensor_cores_matches_per_sequence_oracle(n_seq):
     """2..16 rows per step: projections run as tcgen05 skinny GEMMs (hi/lo bf16 split of the fp32 activations)."""
     po = _po()
