@@ -178,7 +178,10 @@ def run_8b_tp(args):
     if world > 1:
         dist.broadcast(idt, 0)
     nccl_id = bytes(idt.cpu().numpy().tobytes()) if world > 1 else None
-    arch = synth.preset("8b")
+    big = args.workload == "70b-tp"
+    arch = synth.preset("70b" if big else "8b")
+    model_name = "llama-3.1-70b" if big else "llama-3.1-8b"
+    cfg_idx = 4 if big else 3
     max_positions = ctx0 + 2 * (K + W) + 64
     eng = _capi.Engine(arch, _host.rope_table(arch, max_positions), max_batch=B, max_positions=max_positions, page_size=PAGE,
                        max_prefill_tokens=64, device=local, tp_rank=rank, tp_size=world, nccl_id=nccl_id)
@@ -234,9 +237,12 @@ def run_8b_tp(args):
             "metric": "decode_tokens_per_s", "value": value, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"llama-3.1-8b bf16 tensor-parallel decode, batch {B}, context {ctx0} (BASELINE configs[3])",
+            "config": {"workload": f"{model_name} bf16 tensor-parallel decode, batch {B}, context {ctx0} (BASELINE configs[{cfg_idx}])",
                        "batch": B, "context": [ctx0, ctx0 + K], "parallelism": f"tp{world}", "kv": "paged bf16 (synthetic zeros), page 16",
-                       "collective": "ncclAllReduce fp32 sum after O-proj and down-proj (64 per token) + (value,index) all-gather for argmax",
+                       "collective": ("row-parallel partial sums stored into the peers' NVLink-mapped slabs by the projection epilogue "
+                                      "(no all-reduce call)" if info.tp_transport == 2 else
+                                      "ncclAllReduce fp32 sum after O-proj and down-proj" if info.tp_transport == 1 else "none") +
+                                     "; (value,index) all-gather for the vocab-sharded argmax",
                        "l2": "inputs larger than L2", "decode_mode": 0},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "bytes_per_step_per_gpu": bytes_per_step,
@@ -330,7 +336,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--decode-mode", type=int, default=None)
-    ap.add_argument("--workload", default="1b-decode", choices=["1b-decode", "8b-tp", "3b-b8"],
+    ap.add_argument("--workload", default="1b-decode", choices=["1b-decode", "8b-tp", "70b-tp", "3b-b8"],
                     help="1b-decode: BASELINE configs[1], N replicas (default). 8b-tp: configs[3], Llama-3.1-8B tensor-parallel over N GPUs")
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--context", type=int, default=4096)
@@ -338,7 +344,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    if args.workload == "8b-tp":
+    if args.workload in ("8b-tp", "70b-tp"):
         return run_8b_tp(args)
     if args.workload == "3b-b8":
         return run_3b_b8(args)

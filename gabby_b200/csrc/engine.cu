@@ -18,6 +18,7 @@
 #include "gemm_tcgen05.cuh"
 #include "flash_prefill.cuh"
 #include "skinny_gemm.cuh"
+#include "attn_decode_mma.cuh"
 #include "synth.cuh"
 
 using namespace b2l;
@@ -243,6 +244,28 @@ void attn_launch_hd(b2l_ctx* c, const AttnArgs& a, int R) {
     const int want = std::min(32, (3 * c->prop.multiProcessorCount + c->nkv_l * R - 1) / (c->nkv_l * R));
     static const int forced = std::getenv("B2L_ATTN_SPLITS") ? std::atoi(std::getenv("B2L_ATTN_SPLITS")) : 0;   // tuning knob
     const dim3 grid(std::max(1, std::min(c->nsplit, forced > 0 ? forced : want)), c->nkv_l, R), block(kAttnThreads);
+    static const bool use_mma = !(std::getenv("B2L_ATTN_MMA") && std::atoi(std::getenv("B2L_ATTN_MMA")) == 0);
+    if constexpr (HD >= 64) {
+        if (use_mma) {   // tensor-core kernel (attn_decode_mma.cuh); B2L_ATTN_MMA=0 selects the CUDA-core kernel
+            constexpr size_t smem = attn_mma_smem<HD>();
+            auto go = [&](auto kern) {
+                static bool configured = false;
+                if (!configured) {
+                    B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    configured = true;
+                }
+                launch(c, kern, grid, block, smem, a);
+            };
+            switch (c->group) {
+                case 1: go(attn_decode_mma_kernel<HD, 1>); return;
+                case 2: go(attn_decode_mma_kernel<HD, 2>); return;
+                case 3: go(attn_decode_mma_kernel<HD, 3>); return;
+                case 4: go(attn_decode_mma_kernel<HD, 4>); return;
+                case 8: go(attn_decode_mma_kernel<HD, 8>); return;
+                default: throw Error("unsupported GQA group size (heads per kv head must be 1,2,3,4 or 8)");
+            }
+        }
+    }
     switch (c->group) {
         case 1: launch(c, attn_decode_kernel<HD, 1>, grid, block, 0, a); break;
         case 2: launch(c, attn_decode_kernel<HD, 2>, grid, block, 0, a); break;
