@@ -20,6 +20,7 @@ def _n_gpus():
 @pytest.mark.parametrize("preset,layers,seed,transport", [
     ("tiny128", None, 77, "peer"), ("tiny", None, 1234, "peer"), ("tiny128", None, 77, "nccl"),
     ("1b", 2, 5, "peer"),      # full 1B width: batch 2 runs the tcgen05 skinny GEMMs, whose reduce kernel does the sends
+    ("8b", 2, 9, "peer"),      # Llama-3.1-8B width, 2 layers (BASELINE configs[3] shapes: H 4096, I/2 = 7168, hd 128, untied head)
 ])
 def test_tp2_matches_oracle_and_single_gpu(preset, layers, seed, transport):
     if _n_gpus() < 2:
