@@ -696,7 +696,7 @@ void mega_setup(b2l_ctx* c) {
     if (c->nkv_l > G) return no("more kv heads than SMs");
     c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
     const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
-    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 64 + 128 + 4 * 2 * kMegaConsumerWarps * kMegaRows + sizeof(float) * kMegaXsFloats + 2 * static_cast<size_t>(c->H) + 48 * ph.size() + attn_scratch + 256;
+    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 64 + 128 + 4 * 2 * kMegaConsumerWarps * kMegaRows + sizeof(float) * kMegaXsFloats + 2 * static_cast<size_t>(c->H) + (48 + 8) * ph.size() + 16 + attn_scratch + 256;
     int max_smem = 0;
     B2L_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->p.device));
     const int stages = std::min<int>(kMegaMaxStages, static_cast<int>((static_cast<size_t>(max_smem) - fixed) / kMegaStageBytes));
@@ -776,6 +776,7 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     a.ll_h = c->mega_ll_h; a.ll_qkv = c->mega_ll_qkv; a.ll_act = c->mega_ll_act; a.ll_pacc = c->mega_ll_pacc;
     a.ll_pml = c->mega_ll_pml; a.ll_keys = c->mega_ll_keys;
     a.seq_base = c->mega_seq;
+    a.poll_sleep_ns = std::getenv("B2L_MEGA_POLL_NS") ? std::atoi(std::getenv("B2L_MEGA_POLL_NS")) : 0;
     a.ll_use_sentinel = std::getenv("B2L_MEGA_SENTINEL") ? std::atoi(std::getenv("B2L_MEGA_SENTINEL")) : 0;
     if (c->mega_ll) c->mega_seq += static_cast<uint32_t>(n_steps) * static_cast<uint32_t>(c->mega_n_phases);
     int* dev_abort = nullptr;

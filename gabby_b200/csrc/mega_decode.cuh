@@ -78,6 +78,7 @@ struct MegaArgs {
     // reader polls for the sequence number of the phase that produces its input -- no grid barrier anywhere
     unsigned long long *ll_h, *ll_qkv, *ll_act, *ll_pacc, *ll_pml, *ll_keys;
     uint32_t seq_base;  // sequence numbers used by earlier launches
+    int poll_sleep_ns;    // back-off between failed polls of the dataflow words
     int ll_use_sentinel;  // 1: one lane per warp polls first, then everybody loads; 0: everybody polls its own words
     unsigned long long* prof;  // optional [9][n_phases + 1], see b2l_debug_mega_profile globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
 };
@@ -250,7 +251,7 @@ __device__ __forceinline__ void ll_ld8n(const unsigned long long* const (&p)[N],
             }
             return;
         }
-        __nanosleep(64);
+        __nanosleep(c_mega.poll_sleep_ns);
         if (++spins > (1u << 22)) mega_die(abort_flag, code);
     }
 }
@@ -262,7 +263,7 @@ __device__ __forceinline__ void ll_ld4(const unsigned long long* p, uint32_t seq
             v = make_float4(__uint_as_float(w0.x), __uint_as_float(w0.z), __uint_as_float(w1.x), __uint_as_float(w1.z));
             return;
         }
-        __nanosleep(64);
+        __nanosleep(c_mega.poll_sleep_ns);
         if (++spins > (1u << 22)) mega_die(abort_flag, code);
     }
 }
@@ -305,6 +306,8 @@ struct MegaSmem {
 // a phase descriptor held in registers (read from the shared-memory copy)
 struct PhaseRegs {
     int type, layer, N, K, ks, m;
+    int r0, r1;              // this CTA's row range of the phase (precomputed once per launch: the 64-bit divisions of
+                             // mega_row_range cost ~300 instructions at every phase entry)
     const uint16_t* W;
     const uint16_t* norm_w;
     uint16_t* kv_pool;
@@ -323,6 +326,9 @@ __device__ __forceinline__ PhaseRegs mega_load_phase(uint32_t phases, int pi) {
     r.K = static_cast<int>(a2.y);
     r.ks = static_cast<int>(a2.z);
     r.m = static_cast<int>(a2.w);
+    unsigned long long rr = lds64(phases + c_mega.n_phases * 48 + pi * 8);
+    r.r0 = static_cast<int>(rr & 0xffffffffull);
+    r.r1 = static_cast<int>(rr >> 32);
     return r;
 }
 
@@ -460,7 +466,7 @@ __device__ __forceinline__ void mega_attn_combine8_ll(int k, int nsplit, uint32_
                 }
                 break;
             }
-            __nanosleep(64);
+            __nanosleep(c_mega.poll_sleep_ns);
             if (++spins > (1u << 22)) mega_die(a.abort_flag, 120);
         }
 #pragma unroll
@@ -565,7 +571,8 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
 
     // ---- static prologue: nothing here depends on other CTAs, so it overlaps the barrier wait ----
     int r0, r1;
-    mega_row_range(ph.N, type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
+    r0 = ph.r0;
+    r1 = ph.r1;
     if (ph.norm_w) {
         // RMSNorm weight -> shared memory, asynchronously (no registers held across the input poll, no scoreboard wait)
         for (int k = tid * 8; k < K; k += kMegaConsumerThreads * 8)
@@ -631,7 +638,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                                          "f"(__uint_as_float(wd[j].z)) : "memory");
                         break;
                     }
-                    __nanosleep(64);
+                    __nanosleep(c_mega.poll_sleep_ns);
                     if (++spins > (1u << 22)) mega_die(a.abort_flag, 150 + type);
                 }
             }
@@ -1156,8 +1163,8 @@ struct ChunkCursor {
             }
             const PhaseRegs ph = mega_load_phase(phases, pi);
             if (ph.type != PH_ATTN) {
-                int r0;
-                mega_row_range(ph.N, ph.type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
+                const int r0 = ph.r0;
+                r1 = ph.r1;
                 if (r0 < r1) {
                     row = r0;
                     RC = mega_rows_per_stage(ph.ks);
@@ -1198,7 +1205,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     sm.part = p;  p += 4 * 2 * kMegaConsumerWarps * kMegaRows;
     sm.xs = p;    p += 4 * kMegaXsFloats;
     sm.nw = p;    p += 2 * static_cast<uint32_t>(a.H);
-    sm.phases = p; p += 48 * static_cast<uint32_t>(a.n_phases);
+    sm.phases = p; p += (48 + 8) * static_cast<uint32_t>(a.n_phases);   // descriptors, then this CTA's (r0, r1) per phase
+    p = (p + 15u) & ~15u;
     sm.attn_scratch = p;
 
     const int tid = threadIdx.x;
@@ -1216,6 +1224,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
             const uint4 v = __ldg(src + i);
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sm.phases + i * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
         }
+    }
+    for (int i = tid; i < a.n_phases; i += kMegaThreads) {   // row ranges of this CTA, once per launch
+        const MegaPhase& mp = a.phases[i];
+        int r0 = 0, r1 = 0;
+        if (mp.type != PH_ATTN) mega_row_range(mp.N, mp.type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
+        sts64(sm.phases + a.n_phases * 48 + i * 8, static_cast<unsigned long long>(static_cast<unsigned>(r0)) | (static_cast<unsigned long long>(static_cast<unsigned>(r1)) << 32));
     }
     __syncthreads();
 
