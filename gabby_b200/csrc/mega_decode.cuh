@@ -163,6 +163,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
+// ptxas is free to reorder plain shared loads; it serialised the weight loads row by row (one destination register,
+// every FFMA2 chain waiting on its own load). Volatile loads keep the program order: a full step of prefetch.
+__device__ __forceinline__ uint4 lds128_ordered(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
     float4 r;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
@@ -816,12 +823,14 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
 #endif
             uint4 wv[2][kMegaRows];
 #pragma unroll
-            for (int t = 0; t < kMegaRows; t++) wv[0][t] = lds128(row_addr[t]);
+            for (int t = 0; t < kMegaRows; t++) wv[0][t] = lds128_ordered(row_addr[t]);
 #pragma unroll
             for (int i = 0; i < M; i++) {
                 if (i + 1 < M) {
 #pragma unroll
-                    for (int t = 0; t < kMegaRows; t++) wv[(i + 1) & 1][t] = lds128(row_addr[t] + (i + 1) * 512);
+                    for (int t = 0; t < kMegaRows; t++) wv[(i + 1) & 1][t] = lds128_ordered(row_addr[t] + (i + 1) * 512);
+                    __syncwarp();   // scheduling fence: the next step's loads are ISSUED before this step's FFMA2s (ptxas otherwise
+                                    // sinks every load to just before its first use and the loop runs at shared-memory latency)
                 }
 #pragma unroll
                 for (int t = 0; t < kMegaRows; t++) {
