@@ -821,20 +821,24 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
 #ifdef MEGA_PROF_ROUNDS
             pr_t1 = clock64();
 #endif
-            uint4 wv[2][kMegaRows];
+            uint4 wv[3][kMegaRows];   // two steps of prefetch
 #pragma unroll
             for (int t = 0; t < kMegaRows; t++) wv[0][t] = lds128_ordered(row_addr[t]);
+            if (M > 1) {
+#pragma unroll
+                for (int t = 0; t < kMegaRows; t++) wv[1][t] = lds128_ordered(row_addr[t] + 512);
+            }
 #pragma unroll
             for (int i = 0; i < M; i++) {
-                if (i + 1 < M) {
+                if (i + 2 < M) {
 #pragma unroll
-                    for (int t = 0; t < kMegaRows; t++) wv[(i + 1) & 1][t] = lds128_ordered(row_addr[t] + (i + 1) * 512);
-                    __syncwarp();   // scheduling fence: the next step's loads are ISSUED before this step's FFMA2s (ptxas otherwise
-                                    // sinks every load to just before its first use and the loop runs at shared-memory latency)
+                    for (int t = 0; t < kMegaRows; t++) wv[(i + 2) % 3][t] = lds128_ordered(row_addr[t] + (i + 2) * 512);
                 }
+                __syncwarp();   // scheduling fence: later steps' loads are ISSUED before this step's FFMA2s (ptxas otherwise
+                                // sinks every load to just before its first use and the loop runs at shared-memory latency)
 #pragma unroll
                 for (int t = 0; t < kMegaRows; t++) {
-                    const uint4 v = wv[i & 1][t];
+                    const uint4 v = wv[i % 3][t];
                     float2 s2 = acc[t];  // packed fp32x2 FMA (FFMA2): even elements in .x, odd in .y
                     s2 = __ffma2_rn(make_float2(bf16lo(v.x), bf16hi(v.x)), make_float2(xr[i * 8 + 0], xr[i * 8 + 1]), s2);
                     s2 = __ffma2_rn(make_float2(bf16lo(v.y), bf16hi(v.y)), make_float2(xr[i * 8 + 2], xr[i * 8 + 3]), s2);
