@@ -423,8 +423,8 @@ def main():
     achieved = bytes_per_token / (ms_per_step * 1e-3) / 1e9
     mega = eng.info().decode_mode == 1
     # dram__bytes_read.sum + dram__bytes_write.sum of the megakernel from the committed ncu --set full capture
-    # (profiles/r01_megakernel_ncu_summary.txt: 9.9616 GB for a 4-token launch of this exact workload), per launch
-    ncu_dram_bytes_per_token = 9.9616e9 / 4
+    # (profiles/r01_megakernel_ncu_summary.txt: 9.9436 GB for a 4-token launch of this exact workload), per launch
+    ncu_dram_bytes_per_token = 9.9436e9 / 4
     traffic = ncu_dram_bytes_per_token * K if (mega and CTX0 == 512 and arch.hidden_size == 2048 and arch.num_hidden_layers == 16) else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu), same launch as algorithmic_bytes_per_launch",
