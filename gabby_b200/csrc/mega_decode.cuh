@@ -201,6 +201,24 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 }
 
 // rows [r0, r1) of an N-row matrix owned by CTA `c` of `G` (unit = 2 rows for SwiGLU pairs)
+// Loads that must be ISSUED where they are written (ahead of a wait they are meant to overlap): __ldcg / __ldg are
+// non-volatile asm without a memory clobber, and the compiler sinks them to their first use -- i.e. to AFTER the wait.
+__device__ __forceinline__ uint4 ld_cg_early(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_cg_early_f32(const void* p) {
+    float r;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ int ld_nc_early_s32(const void* p) {
+    int r;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+
 // ---- dataflow words: {value, seq} in one 8-byte store; a 16-byte load brings two adjacent words ----
 __device__ __forceinline__ void ll_st(unsigned long long* p, float v, uint32_t seq) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((static_cast<unsigned long long>(seq) << 32) | __float_as_uint(v)) : "memory");
@@ -779,7 +797,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         const bool row_live = live && row_t < r1;
         float resid = 0.f;  // residual input, fetched before the wait so its L2 latency overlaps
         if (out_lane && row_live && q == 0) {
-            if (resid_h) resid = LL ? __ldcg(reinterpret_cast<const float*>(a.ll_h + ll_perm(row_t))) : __ldcg(a.h + row_t);
+            if (resid_h) resid = LL ? ld_cg_early_f32(a.ll_h + ll_perm(row_t)) : ld_cg_early_f32(a.h + row_t);
             else if (resid_e) resid = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row_t]);
         }
         float2 acc[kMegaRows];
@@ -981,7 +999,7 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
-            page[u] = j < j1 ? __ldg(a.block_table + j / a.page_size) : 0;
+            page[u] = j < j1 ? ld_nc_early_s32(a.block_table + j / a.page_size) : 0;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -990,8 +1008,8 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
             vw[u] = make_uint4(0, 0, 0, 0);
             if (j < j1 && j != pos) {
                 const int off = j % a.page_size;
-                kw[u] = __ldcg(reinterpret_cast<const uint4*>(kv.at(page[u], 0, off) + kvh * HD + sl * 8));
-                vw[u] = __ldcg(reinterpret_cast<const uint4*>(kv.at(page[u], 1, off) + kvh * HD + sl * 8));
+                kw[u] = ld_cg_early(kv.at(page[u], 0, off) + kvh * HD + sl * 8);
+                vw[u] = ld_cg_early(kv.at(page[u], 1, off) + kvh * HD + sl * 8);
             }
         }
     };
@@ -1046,26 +1064,51 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
                 }
             }
         }
+        // all U scores first (independent dot products and shuffle trees), then ONE online-softmax update per block:
+        // the per-token update was a serial chain of exp / max / rescale per token
+        float sc[U][GROUP];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const float kf[8] = {bf16lo(kw[u].x), bf16hi(kw[u].x), bf16lo(kw[u].y), bf16hi(kw[u].y), bf16lo(kw[u].z), bf16hi(kw[u].z), bf16lo(kw[u].w), bf16hi(kw[u].w)};
-            const float vf[8] = {bf16lo(vw[u].x), bf16hi(vw[u].x), bf16lo(vw[u].y), bf16hi(vw[u].y), bf16lo(vw[u].z), bf16hi(vw[u].z), bf16lo(vw[u].w), bf16hi(vw[u].w)};
 #pragma unroll
             for (int g = 0; g < GROUP; g++) {
-                float s = 0.f;
+                float d = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; i++) s = fmaf(q[g][i], kf[i], s);
-#pragma unroll
-                for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (valid[u]) {
-                    const float mn = fmaxf(m[g], s);
-                    const float corr = __expf(m[g] - mn), p = __expf(s - mn);
-                    l[g] = l[g] * corr + p;
-#pragma unroll
-                    for (int i = 0; i < 8; i++) acc[g][i] = fmaf(acc[g][i], corr, p * vf[i]);
-                    m[g] = mn;
-                }
+                for (int i = 0; i < 8; i++) d = fmaf(q[g][i], kf[i], d);
+                sc[u][g] = d;
             }
+        }
+#pragma unroll
+        for (int o = LPT / 2; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int g = 0; g < GROUP; g++) sc[u][g] += __shfl_xor_sync(0xffffffffu, sc[u][g], o);
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < GROUP; g++) {
+            float mn = m[g];
+#pragma unroll
+            for (int u = 0; u < U; u++) mn = valid[u] ? fmaxf(mn, sc[u][g]) : mn;
+            if (mn == -INFINITY) continue;   // nothing valid yet in this lane group
+            const float corr = __expf(m[g] - mn);
+            float pu[U], ps = 0.f;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                pu[u] = valid[u] ? __expf(sc[u][g] - mn) : 0.f;
+                ps += pu[u];
+            }
+            l[g] = l[g] * corr + ps;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[g][i] *= corr;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const float vf[8] = {bf16lo(vw[u].x), bf16hi(vw[u].x), bf16lo(vw[u].y), bf16hi(vw[u].y), bf16lo(vw[u].z), bf16hi(vw[u].z), bf16lo(vw[u].w), bf16hi(vw[u].w)};
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[g][i] = fmaf(pu[u], vf[i], acc[g][i]);
+            }
+            m[g] = mn;
         }
     }
     if (pcol) ak2 = clock64();

@@ -8,11 +8,12 @@ from gabby_b200 import synth
 arch = synth.preset("1b")
 eng = bench.build_engine(arch, 0, 1024)
 bt = np.arange(eng.max_blocks, dtype=np.int32)[None, :]
-prompt = synth.synth_prompt(512, arch.vocab_size, arch.bos_token_id, 7)
+CTX = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+prompt = synth.synth_prompt(CTX, arch.vocab_size, arch.bos_token_id, 7)
 first = eng.prefill([prompt], [0], bt)
 eng.mega_profile(True)
-eng.decode_loop(first, [512], bt, 8)
-ids, ms = eng.decode_loop(first, [512], bt, 64)
+eng.decode_loop(first, [CTX], bt, 8)
+ids, ms = eng.decode_loop(first, [CTX], bt, 64)
 ns, types = eng.mega_profile(True)
 n = len(types)
 ns = ns[:, :n].astype(np.int64)
