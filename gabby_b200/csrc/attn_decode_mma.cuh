@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_mma_kernel(const Att
             L = fmaf(__ldcg(a.part_ml + ((rbase + s2) * GROUP + g) * 2 + 1), w, L);
             A = fmaf(__ldcg(a.part_acc + ((rbase + s2) * GROUP + g) * HD + d), w, A);
         }
-        a.out[static_cast<size_t>(r) * a.ldo + (kvh * GROUP + g) * HD + d] = A / L;
+        attn_store_out(a, r, (kvh * GROUP + g) * HD + d, A / L);
     }
 }
 

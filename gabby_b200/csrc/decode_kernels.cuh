@@ -250,7 +250,20 @@ struct AttnArgs {
     float* out;        // [R][ldo]  (heads concatenated)
     int ldo;
     float scale;
+    // optional: also write the output as bf16 hi/lo rows, the B operand of the tcgen05 O-projection (skinny_gemm.cuh):
+    // row r -> split_out[r][ldo], row split_T + r -> the low parts
+    uint16_t* split_out = nullptr;
+    int split_T = 0;
 };
+
+__device__ __forceinline__ void attn_store_out(const AttnArgs& a, int r, int col, float v) {
+    a.out[static_cast<size_t>(r) * a.ldo + col] = v;
+    if (a.split_out) {
+        const uint16_t hi = f32_to_bf16_bits(v);
+        a.split_out[static_cast<size_t>(r) * a.ldo + col] = hi;
+        a.split_out[static_cast<size_t>(a.split_T + r) * a.ldo + col] = f32_to_bf16_bits(v - bf16_bits_to_f32(hi));
+    }
+}
 
 constexpr int kAttnThreads = 128;
 constexpr int kAttnWarps = kAttnThreads / 32;
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const AttnArg
             L = fmaf(__ldcg(a.part_ml + ((rbase + s) * GROUP + g) * 2 + 1), w, L);
             A = fmaf(__ldcg(a.part_acc + ((rbase + s) * GROUP + g) * HD + d), w, A);
         }
-        a.out[static_cast<size_t>(r) * a.ldo + (kvh * GROUP + g) * HD + d] = A / L;
+        attn_store_out(a, r, (kvh * GROUP + g) * HD + d, A / L);
     }
 }
 

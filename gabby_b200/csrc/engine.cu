@@ -317,13 +317,17 @@ void skinny_setup(b2l_ctx* c) {
 // y (op)= W x for R >= 2 activation rows, 32 rows per pass: prep (hi/lo bf16 [+ RMSNorm]) -> tcgen05 skinny GEMM -> split
 // reduce + epilogue
 void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, int ldx, const uint16_t* norm_w, uint16_t* xbuf,
-                   float* y, int ldy, int mode, int R_all, const TpSend* tps = nullptr) {
+                   float* y, int ldy, int mode, int R_all, const TpSend* tps = nullptr, bool x_presplit = false,
+                   uint16_t* split_next = nullptr) {
+    // x_presplit: the producer of x already wrote the bf16 hi/lo rows into xbuf (R_all <= 32 only)
+    // split_next (mode 2 only): write the SwiGLU output as bf16 hi/lo rows for the next projection instead of fp32
     for (int r0 = 0; r0 < R_all; r0 += 32) {
         const int R = std::min(32, R_all - r0);
         const float* xg = x + static_cast<size_t>(r0) * ldx;
         float* yg = y ? y + static_cast<size_t>(r0) * ldy : nullptr;
         const int BT = R <= 8 ? 16 : R <= 16 ? 32 : 64, T = BT / 2;
-        if (norm_w) launch(c, split_bf16_kernel<true>, dim3(R), dim3(256), 0, xg, ldx, norm_w, xbuf, K, T, c->p.rms_norm_eps);
+        if (x_presplit) { /* nothing: xbuf is ready */ }
+        else if (norm_w) launch(c, split_bf16_kernel<true>, dim3(R), dim3(256), 0, xg, ldx, norm_w, xbuf, K, T, c->p.rms_norm_eps);
         else launch(c, split_bf16_kernel<false>, dim3(R), dim3(256), 0, xg, ldx, static_cast<const uint16_t*>(nullptr), xbuf, K, T, 0.f);
         const int n_tiles = (N + 127) / 128, n_kblocks = K / kGemmBK;
         // two CTAs per SM are resident: size the K split so the grid is (at most) one full wave
@@ -339,7 +343,8 @@ void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, 
         const int cols = mode == 2 ? N / 2 : N;
         TpSend send = tps ? *tps : TpSend{};
         for (int p = 0; p < send.tp; p++) send.dst[p] += static_cast<size_t>(r0) * ldy;
-        launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, yg, ldy, send);
+        launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, yg, ldy, send,
+               split_next, T);
     }
 }
 
@@ -463,20 +468,26 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R);
         else gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
         launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
-        const AttnArgs aa{c->qkv, c->qkv_l, kv, rm, c->part_acc, c->part_ml, c->attn_counters, c->attn, c->qd_l, scale};
+        const bool fuse = sk && R <= 32;   // one row group: producers write the next projection's bf16 hi/lo operand directly
+        const int skT = R <= 8 ? 8 : R <= 16 ? 16 : 32;
+        AttnArgs aa{c->qkv, c->qkv_l, kv, rm, c->part_acc, c->part_ml, c->attn_counters, c->attn, c->qd_l, scale};
+        if (fuse) {
+            aa.split_out = c->sk_xq;
+            aa.split_T = skT;
+        }
         attn_launch(c, aa, R);
         const bool tp = c->p.tp_size > 1;
         // O projection (+ residual); under TP every rank holds a K slice and the partial products are summed over NVLink
         const bool peer = tp && c->tp_peer_ok;
         const TpSend send0 = peer ? tp_send_args(c, 0) : TpSend{}, send1 = peer ? tp_send_args(c, 1) : TpSend{};
         const int omode = peer ? 3 : tp ? 0 : 1;
-        if (sk) skinny_linear(c, w.w_o, c->H, c->qd_l, c->attn, c->qd_l, nullptr, c->sk_xq, tp ? c->proj : c->h, c->H, omode, R, &send0);
+        if (sk) skinny_linear(c, w.w_o, c->H, c->qd_l, c->attn, c->qd_l, nullptr, c->sk_xq, tp ? c->proj : c->h, c->H, omode, R, &send0, fuse);
         else gemv(c, w.w_o, c->attn, c->qd_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->qd_l, omode, R, &send0);
         if (peer) tp_ll_reduce(c, 0, R);
         else if (tp) tp_allreduce_add(c, R);
-        if (sk) skinny_linear(c, w.w_gu, 2 * c->I_l, c->H, c->h, c->H, w.post_norm, c->sk_xh, c->act, c->I_l, 2, R);
+        if (sk) skinny_linear(c, w.w_gu, 2 * c->I_l, c->H, c->h, c->H, w.post_norm, c->sk_xh, c->act, c->I_l, 2, R, nullptr, false, fuse ? c->sk_xi : nullptr);
         else gemv(c, w.w_gu, c->h, c->H, c->act, c->I_l, w.post_norm, 2 * c->I_l, c->H, 2, R);
-        if (sk) skinny_linear(c, w.w_down, c->H, c->I_l, c->act, c->I_l, nullptr, c->sk_xi, tp ? c->proj : c->h, c->H, omode, R, &send1);
+        if (sk) skinny_linear(c, w.w_down, c->H, c->I_l, c->act, c->I_l, nullptr, c->sk_xi, tp ? c->proj : c->h, c->H, omode, R, &send1, fuse);
         else gemv(c, w.w_down, c->act, c->I_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->I_l, omode, R, &send1);
         if (peer) tp_ll_reduce(c, 1, R);
         else if (tp) tp_allreduce_add(c, R);

@@ -119,7 +119,7 @@ skinny_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_const
 // y (op)= sum over K splits of partial[split][t][n];  mode 0 store, 1 += (residual), 2 SwiGLU over (2i, 2i+1),
 // 3 = send the sums to every TP rank (tp_send_pair)
 __global__ void skinny_reduce_kernel(const float* __restrict__ partial, int ksplit, int T, int N, int R, int mode,
-                                     float* __restrict__ y, int ldy, const TpSend tps) {
+                                     float* __restrict__ y, int ldy, const TpSend tps, uint16_t* __restrict__ split_out, int split_T) {
     pdl_launch_dependents();
     pdl_wait();
     const int t = blockIdx.y;
@@ -143,7 +143,14 @@ __global__ void skinny_reduce_kernel(const float* __restrict__ partial, int kspl
             g += p.x;
             u += p.y;
         }
-        y[static_cast<size_t>(t) * ldy + i] = (g / (1.0f + __expf(-g))) * u;
+        const float v = (g / (1.0f + __expf(-g))) * u;
+        if (split_out) {   // straight into the next projection's B operand (bf16 hi / lo rows): no fp32 round trip, no split kernel
+            const uint16_t hi = f32_to_bf16_bits(v);
+            split_out[static_cast<size_t>(t) * ldy + i] = hi;
+            split_out[static_cast<size_t>(split_T + t) * ldy + i] = f32_to_bf16_bits(v - bf16_bits_to_f32(hi));
+        } else {
+            y[static_cast<size_t>(t) * ldy + i] = v;
+        }
     } else {
         if (i >= N) return;
         float acc = 0.f;
