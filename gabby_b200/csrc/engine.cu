@@ -318,7 +318,8 @@ void skinny_setup(b2l_ctx* c) {
 // reduce + epilogue
 void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, int ldx, const uint16_t* norm_w, uint16_t* xbuf,
                    float* y, int ldy, int mode, int R_all, const TpSend* tps = nullptr, bool x_presplit = false,
-                   uint16_t* split_next = nullptr) {
+                   uint16_t* split_next = nullptr, const uint16_t* next_norm = nullptr) {
+    // next_norm (mode 1, R_all <= 32, N <= 8192): the residual update is fused with RMSNorm(next_norm) + hi/lo split into split_next
     // x_presplit: the producer of x already wrote the bf16 hi/lo rows into xbuf (R_all <= 32 only)
     // split_next (mode 2 only): write the SwiGLU output as bf16 hi/lo rows for the next projection instead of fp32
     for (int r0 = 0; r0 < R_all; r0 += 32) {
@@ -343,6 +344,11 @@ void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, 
         const int cols = mode == 2 ? N / 2 : N;
         TpSend send = tps ? *tps : TpSend{};
         for (int p = 0; p < send.tp; p++) send.dst[p] += static_cast<size_t>(r0) * ldy;
+        if (mode == 1 && next_norm && split_next) {
+            launch(c, skinny_reduce_norm_split_kernel, dim3(R), dim3(1024), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, yg, next_norm, split_next,
+                   c->p.rms_norm_eps);
+            continue;
+        }
         launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, yg, ldy, send,
                split_next, T);
     }
@@ -465,7 +471,9 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         const LayerWeights& w = c->layers[l];
         const KvLayout kv{w.kv_pool, c->p.page_size, c->kvd_l};
         const bool sk = c->skinny_ok && R >= 2;   // batched decode: projections on the tensor cores
-        if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R);
+        // single GPU, one row group: the residual epilogues of O and down also produce the next projection's normalised operand
+        const bool fuse_norm = sk && R <= 32 && c->p.tp_size == 1 && c->H <= 8192;
+        if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R, nullptr, fuse_norm && l > 0);
         else gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
         launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
         const bool fuse = sk && R <= 32;   // one row group: producers write the next projection's bf16 hi/lo operand directly
@@ -481,13 +489,15 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         const bool peer = tp && c->tp_peer_ok;
         const TpSend send0 = peer ? tp_send_args(c, 0) : TpSend{}, send1 = peer ? tp_send_args(c, 1) : TpSend{};
         const int omode = peer ? 3 : tp ? 0 : 1;
-        if (sk) skinny_linear(c, w.w_o, c->H, c->qd_l, c->attn, c->qd_l, nullptr, c->sk_xq, tp ? c->proj : c->h, c->H, omode, R, &send0, fuse);
+        if (sk) skinny_linear(c, w.w_o, c->H, c->qd_l, c->attn, c->qd_l, nullptr, c->sk_xq, tp ? c->proj : c->h, c->H, omode, R, &send0, fuse,
+                              fuse_norm ? c->sk_xh : nullptr, fuse_norm ? w.post_norm : nullptr);
         else gemv(c, w.w_o, c->attn, c->qd_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->qd_l, omode, R, &send0);
         if (peer) tp_ll_reduce(c, 0, R);
         else if (tp) tp_allreduce_add(c, R);
-        if (sk) skinny_linear(c, w.w_gu, 2 * c->I_l, c->H, c->h, c->H, w.post_norm, c->sk_xh, c->act, c->I_l, 2, R, nullptr, false, fuse ? c->sk_xi : nullptr);
+        if (sk) skinny_linear(c, w.w_gu, 2 * c->I_l, c->H, c->h, c->H, w.post_norm, c->sk_xh, c->act, c->I_l, 2, R, nullptr, fuse_norm, fuse ? c->sk_xi : nullptr);
         else gemv(c, w.w_gu, c->h, c->H, c->act, c->I_l, w.post_norm, 2 * c->I_l, c->H, 2, R);
-        if (sk) skinny_linear(c, w.w_down, c->H, c->I_l, c->act, c->I_l, nullptr, c->sk_xi, tp ? c->proj : c->h, c->H, omode, R, &send1, fuse);
+        if (sk) skinny_linear(c, w.w_down, c->H, c->I_l, c->act, c->I_l, nullptr, c->sk_xi, tp ? c->proj : c->h, c->H, omode, R, &send1, fuse,
+                              fuse_norm ? c->sk_xh : nullptr, fuse_norm ? (l + 1 < c->L ? c->layers[l + 1].in_norm : c->final_norm) : nullptr);
         else gemv(c, w.w_down, c->act, c->I_l, tp ? c->proj : c->h, c->H, nullptr, c->H, c->I_l, omode, R, &send1);
         if (peer) tp_ll_reduce(c, 1, R);
         else if (tp) tp_allreduce_add(c, R);
@@ -499,7 +509,9 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         c->launched++;
     }
     if (want_logits) {
-        if (c->skinny_ok && R >= 2) skinny_linear(c, c->lm_head, c->V_l, c->H, c->h, c->H, c->final_norm, c->sk_xh, c->logits, c->V_l, 0, R);
+        if (c->skinny_ok && R >= 2)
+            skinny_linear(c, c->lm_head, c->V_l, c->H, c->h, c->H, c->final_norm, c->sk_xh, c->logits, c->V_l, 0, R, nullptr,
+                          /*x_presplit: the last down projection already normalised and split h*/ R <= 32 && c->p.tp_size == 1 && c->H <= 8192);
         else gemv(c, c->lm_head, c->h, c->H, c->logits, c->V_l, c->final_norm, c->V_l, c->H, 0, R);
         tp_argmax(c, c->logits, R);
     }

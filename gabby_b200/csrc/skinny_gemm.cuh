@@ -160,6 +160,58 @@ __global__ void skinny_reduce_kernel(const float* __restrict__ partial, int kspl
     }
 }
 
+// Row-parallel projection epilogue fused with the NEXT projection's prologue: h[r] += sum over K splits of partial,
+// then RMSNorm(h[r]) * norm_w -> bf16 hi/lo rows of the next B operand. One CTA per activation row (the norm needs the
+// whole row); replaces skinny_reduce_kernel(mode 1) + split_bf16_kernel<true>.
+__global__ void __launch_bounds__(1024) skinny_reduce_norm_split_kernel(const float* __restrict__ partial, int ksplit, int T, int N,
+                                                                        float* __restrict__ h, const uint16_t* __restrict__ norm_w,
+                                                                        uint16_t* __restrict__ out, float eps) {
+    __shared__ float s_red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.x, tid = threadIdx.x;
+    constexpr int kMaxIter = 4;   // N <= 8192
+    float2 v[kMaxIter];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < kMaxIter; it++) {
+        const int n = it * 2048 + tid * 2;
+        v[it] = make_float2(0.f, 0.f);
+        if (n < N) {
+            float a0 = 0.f, a1 = 0.f;
+            for (int s = 0; s < ksplit; s++) {
+                const float2 p = *reinterpret_cast<const float2*>(partial + (static_cast<size_t>(s) * T + r) * N + n);
+                a0 += p.x;
+                a1 += p.y;
+            }
+            float2* hp = reinterpret_cast<float2*>(h + static_cast<size_t>(r) * N + n);
+            float2 cur = *hp;
+            cur.x += a0;
+            cur.y += a1;
+            *hp = cur;
+            v[it] = cur;
+            ss += cur.x * cur.x + cur.y * cur.y;
+        }
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < 32; i++) tot += s_red[i];
+    const float inv = rsqrtf(tot / static_cast<float>(N) + eps);
+#pragma unroll
+    for (int it = 0; it < kMaxIter; it++) {
+        const int n = it * 2048 + tid * 2;
+        if (n < N) {
+            const uint32_t nw = *reinterpret_cast<const uint32_t*>(norm_w + n);
+            const float y0 = bf16lo(nw) * (v[it].x * inv), y1 = bf16hi(nw) * (v[it].y * inv);
+            const uint16_t h0 = f32_to_bf16_bits(y0), h1 = f32_to_bf16_bits(y1);
+            *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r) * N + n) = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
+            *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(T + r) * N + n) = pack_bf16x2(y0 - bf16_bits_to_f32(h0), y1 - bf16_bits_to_f32(h1));
+        }
+    }
+}
+
 // fp32 rows -> bf16 (hi, lo) rows for the B operand; NORM: fused RMSNorm. out is [2*T][K]: row r = hi, row T + r = lo
 template <bool NORM>
 __global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, const uint16_t* __restrict__ w, uint16_t* __restrict__ out,
