@@ -142,16 +142,36 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvArgs a) {
                 loaded_tile = t;
             }
             if (live) {
-#pragma unroll 4
-                for (int k = lane * 8; k < klen; k += 256) {
-                    const uint4 wa = ldg_stream(w0 + k0 + k);
-                    const uint4 wb = ldg_stream(w1 + k0 + k);
+                // four 256-element steps per iteration: all eight 16-byte weight loads are issued before the first FMA.
+                // (Written as "load, use" per step, ptxas keeps exactly one pair of loads in flight per warp and the
+                // kernel runs at memory latency; the warp-sync is a scheduling fence that keeps the loads ahead.)
+                constexpr int U = 4;
+                for (int kw = 0; kw < klen; kw += 256 * U) {   // warp-uniform trip count: the fence below is a full-warp sync
+                    const int k = kw + lane * 8;
+                    uint4 wa[U], wb[U];
 #pragma unroll
-                    for (int b = 0; b < B; b++) {
-                        const float4 x0 = *reinterpret_cast<const float4*>(xs + b * a.kt + k);
-                        const float4 x1 = *reinterpret_cast<const float4*>(xs + b * a.kt + k + 4);
-                        acc0[b] = dot8(wa, x0, x1, acc0[b]);
-                        acc1[b] = dot8(wb, x0, x1, acc1[b]);
+                    for (int u = 0; u < U; u++) {
+                        const int kk = k + u * 256;
+                        wa[u] = make_uint4(0, 0, 0, 0);
+                        wb[u] = make_uint4(0, 0, 0, 0);
+                        if (kk < klen) {
+                            wa[u] = ldg_stream(w0 + k0 + kk);
+                            wb[u] = ldg_stream(w1 + k0 + kk);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int kk = k + u * 256;
+                        if (kk < klen) {
+#pragma unroll
+                            for (int b = 0; b < B; b++) {
+                                const float4 x0 = *reinterpret_cast<const float4*>(xs + b * a.kt + kk);
+                                const float4 x1 = *reinterpret_cast<const float4*>(xs + b * a.kt + kk + 4);
+                                acc0[b] = dot8(wa[u], x0, x1, acc0[b]);
+                                acc1[b] = dot8(wb[u], x0, x1, acc1[b]);
+                            }
+                        }
                     }
                 }
             }
