@@ -571,16 +571,16 @@ void prefill_gemm(b2l_ctx* c, int T, int n_seq, int tap_row0) {
             FlashArgs fa{c->pf_qkv, c->qkv_l, kv, c->d_block_tables, c->max_blocks_cap, static_cast<const PrefillTile*>(c->pf_tiles),
                          c->pf_attn16, c->qd_l, c->group, scale * 1.4426950408889634f};
             const dim3 grid(c->pf_n_tiles, c->nh_l);
-            if (c->hd == 64) {
-                flash_prefill_kernel<64><<<grid, kFlashThreads, 3 * 64 * (64 + 8) * 2, c->stream>>>(fa);
-            } else {
-                static bool configured = false;
-                if (!configured) {
-                    B2L_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * (128 + 8) * 2));
-                    configured = true;
-                }
-                flash_prefill_kernel<128><<<grid, kFlashThreads, 3 * 64 * (128 + 8) * 2, c->stream>>>(fa);
+            // shared memory: the Q tile + two {K, V} buffers of 64 padded rows each
+            const size_t fsmem = static_cast<size_t>(5) * 64 * (c->hd + 8) * 2;
+            static bool configured = false;
+            if (!configured) {
+                B2L_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * (64 + 8) * 2));
+                B2L_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * (128 + 8) * 2));
+                configured = true;
             }
+            if (c->hd == 64) flash_prefill_kernel<64><<<grid, kFlashThreads, fsmem, c->stream>>>(fa);
+            else flash_prefill_kernel<128><<<grid, kFlashThreads, fsmem, c->stream>>>(fa);
             B2L_CUDA(cudaGetLastError());
             c->launched++;
         } else {

@@ -57,8 +57,7 @@ __global__ void __launch_bounds__(kFlashThreads) flash_prefill_kernel(const Flas
     constexpr int DBLOCKS = HD / 8;       // 8-wide output column blocks
     extern __shared__ __align__(16) uint16_t fsm[];
     uint16_t* sQ = fsm;                        // [64][LDS]
-    uint16_t* sK = sQ + kFlashBM * LDS;        // [64][LDS]
-    uint16_t* sV = sK + kFlashBN * LDS;        // [64][LDS]
+    uint16_t* sKV = sQ + kFlashBM * LDS;       // two buffers of {K [64][LDS], V [64][LDS]}: tile i+1 loads while tile i computes
     const PrefillTile tile = a.tiles[blockIdx.x];
     const int head = blockIdx.y, kvh = head / a.group;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
@@ -85,9 +84,10 @@ __global__ void __launch_bounds__(kFlashThreads) flash_prefill_kernel(const Flas
     const int q_pos0 = tile.pos0 + warp * 16 + gid, q_pos1 = q_pos0 + 8;
     const int kv_end = tile.pos0 + tile.n_rows;                 // tokens [0, kv_end) exist for this tile
 
-    for (int j0 = 0; j0 < kv_end; j0 += kFlashBN) {
-        __syncthreads();  // previous tile fully consumed
-        // ---- gather K and V rows of tokens [j0, j0+64) from their pages ----
+    // gather K and V rows of tokens [j0, j0+64) from their pages into buffer `buf`
+    auto issue_tile = [&](int j0, int buf) {
+        uint16_t* sK = sKV + buf * 2 * kFlashBN * LDS;
+        uint16_t* sV = sK + kFlashBN * LDS;
         for (int i = tid; i < kFlashBN * (HD / 8); i += kFlashThreads) {
             const int r = i / (HD / 8), c = (i % (HD / 8)) * 8;
             const int j = min(j0 + r, kv_end - 1);
@@ -96,8 +96,15 @@ __global__ void __launch_bounds__(kFlashThreads) flash_prefill_kernel(const Flas
             cp_async16(smem_u32(sV + r * LDS + c), a.kv.at(page, 1, off) + kvh * HD + c);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+    };
+    issue_tile(0, 0);
+    int buf = 0;
+    for (int j0 = 0; j0 < kv_end; j0 += kFlashBN, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");   // this tile (the only group in flight) has landed
+        __syncthreads();                                        // ... for every thread, and everybody is done with the other buffer
+        if (j0 + kFlashBN < kv_end) issue_tile(j0 + kFlashBN, buf ^ 1);   // overlaps with the math below
+        const uint16_t* sK = sKV + buf * 2 * kFlashBN * LDS;
+        const uint16_t* sV = sK + kFlashBN * LDS;
 
         // ---- S = Q K^T : 16 x 64 per warp ----
         float s[8][4];
