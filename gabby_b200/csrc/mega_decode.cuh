@@ -902,7 +902,8 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
             // K was split over ks warps: add the slices through smem (one CTA barrier per round)
             const uint32_t part = sm.part + (rd & 1) * (kMegaConsumerWarps * kMegaRows * 4);
             if (out_lane) sts32f(part + (w * kMegaRows + my_t) * 4, row_live ? s : 0.f);
-            consumer_bar();
+            // only the ks warps that share this row group meet (named barrier 2 + group): the other groups stream on
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + rloc), "r"(32 * ks) : "memory");
             if (q != 0) continue;
             s = 0.f;
             for (int i = 0; i < ks; i++) s += lds32f(part + ((w + i) * kMegaRows + my_t) * 4);
