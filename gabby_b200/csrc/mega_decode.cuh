@@ -3,14 +3,37 @@
 //
 //   * one CTA per SM (148), 8 consumer warps + 1 producer warp
 //   * the producer streams this CTA's share of EVERY weight matrix, in model order, through a
-//     6-stage x 32 KB shared-memory ring with TMA bulk copies (cp.async.bulk -> UBLKCP) that
+//     12-stage x 16 KB shared-memory ring with TMA bulk copies (cp.async.bulk -> UBLKCP) that
 //     complete on mbarriers. Weights do not depend on activations, so the stream never stops:
 //     it runs ahead across op, layer and even token boundaries, bounded only by the ring.
 //   * consumers keep the op's input vector in REGISTERS (64 fp32 per lane), dot it against the
-//     bf16 rows as they land, and hand results on through L2; ops are separated by a grid-wide
-//     barrier (one release-atomic per CTA) whose latency the ring hides from HBM.
+//     bf16 rows as they land (ordered ld.shared with a two-step prefetch, FFMA2), and hand the
+//     results on through L2.
 //   * attention (split-K over the paged bf16 cache, RoPE and K/V append fused in), SwiGLU,
 //     residual adds, both RMSNorms, the lm_head argmax and the token feedback are all inside.
+//
+// Hand-off between phases. Two builds of the same kernel (template parameter LL):
+//   LL = true (default, "dataflow"): no grid barrier. Every value that crosses CTAs is an 8-byte
+//     word {fp32 bits, sequence number}; the sequence number names the phase instance that
+//     produced it (seq_base + step * n_phases + phase + 1). A reader polls the words it needs until
+//     they carry the number of the producing phase (always the phase before its own). The flag
+//     travels with the data, so there is no fence and no counter, and a CTA starts a phase as soon
+//     as ITS inputs exist.
+//     Why nothing is overwritten too early (write-after-read): every phase reads the COMPLETE output
+//     of the phase before it. So when some CTA writes an output of phase p+1, it has already seen all
+//     of phase p's outputs, hence every CTA has finished computing phase p, hence every CTA has long
+//     finished LOADING phase p's inputs (a phase loads its input before its first row). A buffer is
+//     therefore safe to rewrite two phases after it was written, and no buffer here is rewritten
+//     sooner: h is written by O-proj and down (read by gate/up resp. the next QKV / lm_head), qkv by
+//     QKV (read by attention), the partials by attention (read by O-proj), act by gate/up (read by
+//     down), the per-CTA argmax keys by lm_head (read at the next token's first phase). Residual
+//     read-modify-writes of h touch only rows the same CTA owns in both O-proj and down.
+//     The only plain (non-word) data that crosses CTAs is the new token's K/V cache line: its
+//     writer fences before publishing its partials, readers fence once per token.
+//     Sequence numbers are 32 bits and never reset (host keeps seq_base across launches); buffers
+//     start at 0, which is never produced.
+//   LL = false: phases are separated by a grid-wide barrier (one release-atomic per CTA + acquire
+//     poll), plain fp32 activations. Kept for comparison (B2L_MEGA_LL=0).
 //
 // HBM sees one sequential read of the model per token; everything else lives in L2 / smem.
 // Math is identical to decode_kernels.cuh (the multi-kernel path) up to fp32 summation order.
