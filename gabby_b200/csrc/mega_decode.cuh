@@ -303,18 +303,6 @@ __device__ __forceinline__ void ll_ld8n(const unsigned long long* const (&p)[N],
         if (++spins > (1u << 22)) mega_die(abort_flag, code);
     }
 }
-__device__ __forceinline__ void ll_ld4(const unsigned long long* p, uint32_t seq, float4& v, int* abort_flag, int code) {
-    unsigned spins = 0;
-    for (;;) {
-        const uint4 w0 = ll_ld2(p), w1 = ll_ld2(p + 2);
-        if (w0.y == seq && w0.w == seq && w1.y == seq && w1.w == seq) {
-            v = make_float4(__uint_as_float(w0.x), __uint_as_float(w0.z), __uint_as_float(w1.x), __uint_as_float(w1.z));
-            return;
-        }
-        __nanosleep(c_mega.poll_sleep_ns);
-        if (++spins > (1u << 22)) mega_die(abort_flag, code);
-    }
-}
 
 __device__ __forceinline__ void mega_row_range(int N, int unit, int c, int G, int& r0, int& r1) {
     const long long units = N / unit;
