@@ -412,7 +412,10 @@ def main():
     e2e_value = world * K / float(e2e_t.item())
     assert e2e_ids == ids[:, 0].tolist(), "device loop and per-step API disagree"
     n_blocks_needed = (CTX0 + K + PAGE - 1) // PAGE
-    h2d = 4 + 4 + 4 + 4 * eng.max_blocks
+    # megakernel single-step path: token + position ride in the kernel-argument upload (8 bytes of payload), the block-table
+    # row (4 * max_blocks bytes) is re-sent only when a new page is appended (every PAGE steps); multi-kernel path: token,
+    # position, slot and the block-table row every step
+    h2d = (8 + 4 * eng.max_blocks / PAGE) if info.decode_mode == 1 else (4 + 4 + 4 + 4 * eng.max_blocks)
     d2h = 4
 
     # ---- roofline ---------------------------------------------------------------------------

@@ -676,7 +676,12 @@ void upload_block_tables(b2l_ctx* c, int n_seq, const int32_t* bt, int max_block
             s[static_cast<size_t>(i) * cap + j] = j < need ? page : 0;
         }
     }
-    B2L_CUDA(cudaMemcpyAsync(c->d_block_tables, s, sizeof(int32_t) * n_seq * cap, cudaMemcpyHostToDevice, c->stream));
+    // a decode step inside a page leaves the tables unchanged: do not pay a copy-engine round trip for it
+    const size_t n = static_cast<size_t>(n_seq) * cap;
+    if (c->bt_uploaded_rows == n_seq && c->bt_uploaded.size() >= n && std::memcmp(c->bt_uploaded.data(), s, n * sizeof(int32_t)) == 0) return;
+    B2L_CUDA(cudaMemcpyAsync(c->d_block_tables, s, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    c->bt_uploaded.assign(s, s + n);
+    c->bt_uploaded_rows = n_seq;
 }
 
 // ---- persistent megakernel (mega_decode.cuh) ------------------------------------------------
@@ -782,7 +787,10 @@ void mega_setup(b2l_ctx* c) {
 }
 
 // n_steps greedy tokens in one cooperative launch; token/position/block table already on the device
-void mega_enqueue(b2l_ctx* c, int n_steps) {
+// host_io (single-step API path): token / position travel in the launch arguments, the result comes back through
+// mapped pinned memory -- no copy-engine operations at all around the launch
+constexpr int kMegaIoWord = 600;   // mega_abort[600..602] = token, position (host side only), result (written by the kernel)
+void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
     B2L_CHECK(c->mega_ok, "megakernel unavailable: " + c->mega_why);
     MegaArgs a{};
     a.phases = static_cast<const MegaPhase*>(c->mega_phases);
@@ -805,6 +813,14 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     int* dev_abort = nullptr;
     B2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_abort), c->mega_abort, 0));
     a.abort_flag = dev_abort;
+    if (host_io) {
+        // token and position ride in the launch arguments (constant memory: many SMs reading one mapped host word over
+        // PCIe serialise, measured +0.25 ms); only the result is a (posted) store into mapped host memory
+        a.arg_io = 1;
+        a.token0 = c->mega_abort[kMegaIoWord];
+        a.pos0 = c->mega_abort[kMegaIoWord + 1];
+        a.out_ids = dev_abort + kMegaIoWord + 2;
+    }
     a.prof = c->mega_prof;
     a.debug_progress = std::getenv("B2L_MEGA_DEBUG") ? 1 : 0;
     a.debug_nostream = std::getenv("B2L_MEGA_NOSTREAM") ? 1 : 0;
@@ -812,7 +828,7 @@ void mega_enqueue(b2l_ctx* c, int n_steps) {
     a.attn_tps = c->mega_attn_tps;
     a.producer_sleep_ns = std::getenv("B2L_MEGA_PSLEEP") ? std::atoi(std::getenv("B2L_MEGA_PSLEEP")) : 100;
     a.l2_ahead = c->mega_l2_ahead;
-    B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));
+    if (!c->mega_ll) B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));   // argmax keys of the barrier build
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->prop.multiProcessorCount);
     cfg.blockDim = dim3(kMegaThreads);
@@ -1220,26 +1236,35 @@ int b2l_decode(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* posi
             slots[i] = i;
             need[i] = positions[i] + 1;
         }
-        upload_rows_meta(c, n_seq, tokens, positions, slots.data());
-        upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
-        bool mega = false;
-        if (c->taps) {
-            c->tap_rows = n_seq;
-            enqueue_forward(c, n_seq, true, 0);
-        } else if (c->decode_mode == 1 && n_seq == 1) {
-            mega = true;
-            mega_enqueue(c, 1);
-            B2L_CUDA(cudaMemcpyAsync(c->d_next_ids, c->d_out_ids, sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+        const bool mega = !c->taps && c->decode_mode == 1 && n_seq == 1;
+        if (mega) {
+            // single-step megakernel call: token and position go in, the id comes back, through mapped pinned memory;
+            // the block table is re-uploaded only when it changed. Stream work = constant upload + one launch.
+            upload_block_tables(c, 1, block_tables, max_blocks, need.data());
+            volatile int* io = c->mega_abort + kMegaIoWord;
+            io[0] = tokens[0];
+            io[1] = positions[0];
+            io[2] = -1;
+            mega_enqueue(c, 1, true);
+            mega_check(c, cudaStreamSynchronize(c->stream));
+            B2L_CHECK(io[2] >= 0, "megakernel returned no token");
+            next_ids[0] = io[2];
         } else {
-            Graph& g = decode_graph(c, n_seq, false);
-            B2L_CUDA(cudaGraphLaunch(g.exec, c->stream));
-            c->launched += g.nodes;
+            upload_rows_meta(c, n_seq, tokens, positions, slots.data());
+            upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
+            if (c->taps) {
+                c->tap_rows = n_seq;
+                enqueue_forward(c, n_seq, true, 0);
+            } else {
+                Graph& g = decode_graph(c, n_seq, false);
+                B2L_CUDA(cudaGraphLaunch(g.exec, c->stream));
+                c->launched += g.nodes;
+            }
+            int32_t* h_next = c->h_stage + 3 * c->max_rows + static_cast<size_t>(c->p.max_batch) * c->max_blocks_cap;
+            B2L_CUDA(cudaMemcpyAsync(h_next, c->d_next_ids, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, c->stream));
+            B2L_CUDA(cudaStreamSynchronize(c->stream));
+            std::memcpy(next_ids, h_next, sizeof(int32_t) * n_seq);
         }
-        int32_t* h_next = c->h_stage + 3 * c->max_rows + static_cast<size_t>(c->p.max_batch) * c->max_blocks_cap;
-        B2L_CUDA(cudaMemcpyAsync(h_next, c->d_next_ids, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, c->stream));
-        if (mega) mega_check(c, cudaStreamSynchronize(c->stream));
-        else B2L_CUDA(cudaStreamSynchronize(c->stream));
-        std::memcpy(next_ids, h_next, sizeof(int32_t) * n_seq);
         c->logits_src = c->logits;
         c->logits_rows = n_seq;
     });

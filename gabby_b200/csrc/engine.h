@@ -106,6 +106,8 @@ struct b2l_ctx {
     unsigned long long *mega_ll_h = nullptr, *mega_ll_qkv = nullptr, *mega_ll_act = nullptr, *mega_ll_pacc = nullptr,
                        *mega_ll_pml = nullptr, *mega_ll_keys = nullptr;
     uint32_t mega_seq = 0;                   // sequence numbers consumed by earlier launches
+    std::vector<int32_t> bt_uploaded;        // image of the block tables currently on the device (skip identical re-uploads)
+    int bt_uploaded_rows = 0;
     int* mega_abort = nullptr;               // pinned host flag, device-visible
     unsigned long long* mega_prof = nullptr; // device [4][n_phases+1] phase timestamps (debug)
 

@@ -82,6 +82,8 @@ struct MegaArgs {
     int* attn_counters;
     int nsplit_max;
     // token loop
+    int32_t token0, pos0;  // arg_io != 0: first token / position travel in this struct (constant memory) instead of *token / *position
+    int arg_io;
     int32_t* token;      // in: first token; out: last argmax
     int32_t* position;   // in: first position; out: advanced
     int32_t* out_ids;    // [n_steps]
@@ -1299,9 +1301,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
         if (mp.type != PH_ATTN) mega_row_range(mp.N, mp.type == PH_GATEUP ? 2 : 1, blockIdx.x, gridDim.x, r0, r1);
         sts64(sm.phases + a.n_phases * 48 + i * 8, static_cast<unsigned long long>(static_cast<unsigned>(r0)) | (static_cast<unsigned long long>(static_cast<unsigned>(r1)) << 32));
     }
+    if (tid == 0 && !a.arg_io) {   // first token and position: one global read per CTA
+        sts32f(sm.red, __int_as_float(*reinterpret_cast<const volatile int32_t*>(a.token)));
+        sts32f(sm.red + 4, __int_as_float(*reinterpret_cast<const volatile int32_t*>(a.position)));
+    }
     __syncthreads();
 
-    const int pos0 = *a.position;
+    const int pos0 = a.arg_io ? a.pos0 : __float_as_int(lds32f(sm.red + 4));
+    const int token0 = a.arg_io ? a.token0 : __float_as_int(lds32f(sm.red));
 
     if (tid >= kMegaConsumerThreads) {
         // ================= producer warp: stream every weight chunk this CTA will ever need =================
@@ -1365,7 +1372,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     st.nbar = 0;
     st.epoch = *a.bar_epoch;
     st.best_key = 0ull;
-    st.token = *a.token;
+    st.token = token0;
     st.step = 0;
     st.need_barrier = false;
     for (int step = 0; step < a.n_steps; step++) {
