@@ -15,6 +15,8 @@ SYMBOLS = [
     "gb_checkpoint_info", "gb_checkpoint_tensor", "gb_kv_create", "gb_kv_free", "gb_kv_new_sequence", "gb_kv_reserve",
     "gb_kv_release", "gb_kv_table", "gb_kv_free_pages", "gb_tokenizer_create", "gb_tokenizer_free", "gb_tokenize",
     "gb_detokenize", "gb_chat_prompt", "gb_argmax",
+    "gb_sched_create_b2l", "gb_sched_create_fake", "gb_sched_free", "gb_sched_submit", "gb_sched_step", "gb_sched_drain",
+    "gb_sched_result", "gb_sched_stats",
 ]
 
 
@@ -74,6 +76,15 @@ def lib():
         L.gb_chat_prompt.argtypes = [vp, C.c_char_p, C.c_char_p, vp, C.c_int, ip]
         L.gb_argmax.argtypes = [vp, C.c_int64]
         L.gb_argmax.restype = C.c_int32
+        L.gb_sched_create_b2l.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.gb_sched_create_fake.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+        L.gb_sched_free.argtypes = [vp]
+        L.gb_sched_free.restype = None
+        L.gb_sched_submit.argtypes = [vp, vp, C.c_int, C.c_int, ip]
+        L.gb_sched_step.argtypes = [vp, ip]
+        L.gb_sched_drain.argtypes = [vp]
+        L.gb_sched_result.argtypes = [vp, C.c_int, vp, C.c_int, ip, ip, ip]
+        L.gb_sched_stats.argtypes = [vp, vp]
         _LIB = L
     return _LIB
 
@@ -203,6 +214,65 @@ class Generator:
     def close(self):
         if getattr(self, "h", None):
             lib().gb_generator_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scheduler:
+    """Continuous batching (gabby_b200/host/scheduler.h). `engine`: a gabby_b200._capi.Engine created with
+    max_batch >= max_batch here (its page pool is managed by this scheduler), or None for the deterministic fake
+    engine (next = (31 * last + 7 * position + 3) mod vocab) used by the CPU policy tests."""
+
+    def __init__(self, engine=None, *, eos_ids=(), max_batch=8, max_positions=2048, max_prefill_tokens=2048, num_pages=0,
+                 page_size=16, fake_vocab=0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        self._engine = engine   # keep the engine alive
+        if engine is None:
+            eos = int(eos_ids[0]) if len(eos_ids) else -1
+            _ck(self.L.gb_sched_create_fake(fake_vocab, eos, max_batch, max_positions, max_prefill_tokens, num_pages, page_size,
+                                            C.byref(self.h)))
+        else:
+            e = np.ascontiguousarray(eos_ids, dtype=np.int32)
+            _ck(self.L.gb_sched_create_b2l(engine.h, e.ctypes.data_as(C.c_void_p), e.size, max_batch, max_positions,
+                                           max_prefill_tokens, num_pages, page_size, C.byref(self.h)))
+
+    def submit(self, prompt, max_new_tokens: int) -> int:
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        rid = C.c_int(-1)
+        _ck(self.L.gb_sched_submit(self.h, p.ctypes.data_as(C.c_void_p), p.size, max_new_tokens, C.byref(rid)))
+        return rid.value
+
+    def step(self) -> int:
+        n = C.c_int(0)
+        _ck(self.L.gb_sched_step(self.h, C.byref(n)))
+        return n.value
+
+    def drain(self):
+        _ck(self.L.gb_sched_drain(self.h))
+
+    def result(self, rid: int):
+        """-> (tokens, finish ('none' | 'stop' | 'length'), done)"""
+        n, fin, done = C.c_int(0), C.c_int(0), C.c_int(0)
+        _ck(self.L.gb_sched_result(self.h, rid, None, 0, C.byref(n), C.byref(fin), C.byref(done)))
+        out = np.zeros(max(1, n.value), dtype=np.int32)
+        _ck(self.L.gb_sched_result(self.h, rid, out.ctypes.data_as(C.c_void_p), out.size, C.byref(n), C.byref(fin), C.byref(done)))
+        return out[:n.value].tolist(), ("none", "stop", "length")[fin.value], bool(done.value)
+
+    def stats(self) -> dict:
+        out = np.zeros(8, dtype=np.int64)
+        _ck(self.L.gb_sched_stats(self.h, out.ctypes.data_as(C.c_void_p)))
+        keys = ("steps", "prefill_calls", "decode_calls", "prefill_tokens", "decode_tokens", "preemptions", "max_concurrent", "free_pages")
+        return dict(zip(keys, out.tolist()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.gb_sched_free(self.h)
             self.h = None
 
     def __del__(self):

@@ -10,6 +10,7 @@
 #include "kv_allocator.h"
 #include "params.h"
 #include "sampler.h"
+#include "scheduler.h"
 #include "tokenizer.h"
 
 using namespace gabby::inference;
@@ -206,5 +207,103 @@ int gb_chat_prompt(gb_tokenizer* t, const char* system_text, const char* user_te
 }
 
 int32_t gb_argmax(const float* logits, int64_t n) { return GreedySampler::Argmax(logits, n); }
+
+namespace {
+// deterministic stand-in for the engine: the next token depends only on (last token, its position), so any batching,
+// admission order or preemption must reproduce the sequential result exactly
+class FakeBatchEngine : public BatchEngine {
+public:
+    explicit FakeBatchEngine(int vocab) : vocab_(vocab) {}
+    int32_t Next(int32_t last, int pos) const { return static_cast<int32_t>((31ll * last + 7ll * pos + 3) % vocab_); }
+    void Prefill(int n_seq, const int32_t* tokens, const int32_t* q_lens, const int32_t* start_pos, const int32_t*, int, int32_t* next_ids) override {
+        int off = 0;
+        for (int i = 0; i < n_seq; i++) {
+            off += q_lens[i];
+            next_ids[i] = Next(tokens[off - 1], start_pos[i] + q_lens[i] - 1);
+        }
+    }
+    void Decode(int n_seq, const int32_t* tokens, const int32_t* positions, const int32_t*, int, int32_t* next_ids) override {
+        for (int i = 0; i < n_seq; i++) next_ids[i] = Next(tokens[i], positions[i]);
+    }
+
+private:
+    int vocab_;
+};
+}  // namespace
+
+struct gb_sched {
+    std::unique_ptr<BatchEngine> engine;
+    std::unique_ptr<KvPageAllocator> kv;
+    std::unique_ptr<BatchScheduler> sched;
+};
+
+static gb_sched* make_sched(std::unique_ptr<BatchEngine> engine, std::vector<int> eos, int max_batch, int max_positions,
+                            int max_prefill_tokens, int num_pages, int page_size) {
+    auto s = std::make_unique<gb_sched>();
+    s->engine = std::move(engine);
+    s->kv = std::make_unique<KvPageAllocator>(num_pages, page_size, (max_positions + page_size - 1) / page_size);
+    SchedulerLimits lim;
+    lim.max_batch = max_batch;
+    lim.max_positions = max_positions;
+    lim.max_prefill_tokens = max_prefill_tokens;
+    s->sched = std::make_unique<BatchScheduler>(s->engine.get(), s->kv.get(), lim, std::move(eos));
+    return s.release();
+}
+
+int gb_sched_create_b2l(void* engine, const int32_t* eos_ids, int n_eos, int max_batch, int max_positions, int max_prefill_tokens,
+                        int num_pages, int page_size, gb_sched** out) {
+    return guarded([&] {
+        if (!engine || !out || (n_eos > 0 && !eos_ids)) throw std::runtime_error("gb_sched_create_b2l: null argument");
+        std::vector<int> eos(eos_ids, eos_ids + std::max(0, n_eos));
+        *out = make_sched(std::make_unique<B2lBatchEngine>(static_cast<b2l_ctx*>(engine)), std::move(eos), max_batch, max_positions,
+                          max_prefill_tokens, num_pages, page_size);
+    });
+}
+int gb_sched_create_fake(int vocab, int eos_id, int max_batch, int max_positions, int max_prefill_tokens, int num_pages,
+                         int page_size, gb_sched** out) {
+    return guarded([&] {
+        if (!out || vocab < 2) throw std::runtime_error("gb_sched_create_fake: bad argument");
+        *out = make_sched(std::make_unique<FakeBatchEngine>(vocab), std::vector<int>{eos_id}, max_batch, max_positions, max_prefill_tokens,
+                          num_pages, page_size);
+    });
+}
+void gb_sched_free(gb_sched* s) { delete s; }
+int gb_sched_submit(gb_sched* s, const int32_t* prompt, int n_prompt, int max_new_tokens, int* id) {
+    return guarded([&] {
+        if (!s || !id || (n_prompt > 0 && !prompt)) throw std::runtime_error("gb_sched_submit: null argument");
+        *id = s->sched->Submit(std::vector<int32_t>(prompt, prompt + std::max(0, n_prompt)), max_new_tokens);
+    });
+}
+int gb_sched_step(gb_sched* s, int* progressed) {
+    return guarded([&] {
+        if (!s) throw std::runtime_error("gb_sched_step: null argument");
+        const int n = s->sched->Step();
+        if (progressed) *progressed = n;
+    });
+}
+int gb_sched_drain(gb_sched* s) {
+    return guarded([&] {
+        if (!s) throw std::runtime_error("gb_sched_drain: null argument");
+        s->sched->Drain();
+    });
+}
+int gb_sched_result(gb_sched* s, int id, int32_t* out, int cap, int* n, int* finish, int* done) {
+    return guarded([&] {
+        if (!s || !n) throw std::runtime_error("gb_sched_result: null argument");
+        const SchedResult& r = s->sched->Result(id);
+        *n = static_cast<int>(r.tokens.size());
+        for (size_t i = 0; out && i < r.tokens.size() && static_cast<int>(i) < cap; i++) out[i] = r.tokens[i];
+        if (finish) *finish = r.finish == FinishReason::kStop ? 1 : r.finish == FinishReason::kLength ? 2 : 0;
+        if (done) *done = r.done ? 1 : 0;
+    });
+}
+int gb_sched_stats(gb_sched* s, int64_t* out) {
+    return guarded([&] {
+        if (!s || !out) throw std::runtime_error("gb_sched_stats: null argument");
+        const SchedulerStats& st = s->sched->stats();
+        out[0] = st.steps; out[1] = st.prefill_calls; out[2] = st.decode_calls; out[3] = st.prefill_tokens;
+        out[4] = st.decode_tokens; out[5] = st.preemptions; out[6] = st.max_concurrent; out[7] = s->kv->free_pages();
+    });
+}
 
 }  // extern "C"

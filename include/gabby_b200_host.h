@@ -73,6 +73,26 @@ int gb_chat_prompt(gb_tokenizer* t, const char* system_text, const char* user_te
 /* GreedySampler::Argmax (first max) on host logits */
 int32_t gb_argmax(const float* logits, int64_t n);
 
+/* ---- continuous batching (gabby_b200/host/scheduler.h). The reference answers one
+ * request at a time (/root/reference/src/service.cc:150 under /root/reference/src/http/thread_pool.cc:22-28); this
+ * queue feeds the engine ragged multi-sequence prefill / decode steps. ---- */
+typedef struct gb_sched gb_sched;
+/* over a real engine: `engine` is the b2l_ctx* (created with max_batch >= the scheduler's); the scheduler owns a
+ * KvPageAllocator over that engine's page pool (num_pages, page_size as given to b2l_create) */
+int gb_sched_create_b2l(void* engine, const int32_t* eos_ids, int n_eos, int max_batch, int max_positions, int max_prefill_tokens,
+                        int num_pages, int page_size, gb_sched** out);
+/* over a deterministic fake engine (next = (31 * last + 7 * position + 3) mod vocab): policy tests without a GPU */
+int gb_sched_create_fake(int vocab, int eos_id, int max_batch, int max_positions, int max_prefill_tokens, int num_pages,
+                         int page_size, gb_sched** out);
+void gb_sched_free(gb_sched* s);
+int gb_sched_submit(gb_sched* s, const int32_t* prompt, int n_prompt, int max_new_tokens, int* id);
+int gb_sched_step(gb_sched* s, int* progressed);
+int gb_sched_drain(gb_sched* s);
+/* finish: 0 none, 1 stop (EOS), 2 length */
+int gb_sched_result(gb_sched* s, int id, int32_t* out, int cap, int* n, int* finish, int* done);
+/* out[8]: steps, prefill_calls, decode_calls, prefill_tokens, decode_tokens, preemptions, max_concurrent, free_pages */
+int gb_sched_stats(gb_sched* s, int64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

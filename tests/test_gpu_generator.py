@@ -80,3 +80,40 @@ def test_generate_request_to_message_and_errors():
         os.remove(os.path.join(d, "tokenizer.json"))              # LoadConfig needs all five JSON files (config.cc:13-17)
         with pytest.raises(_host.HostError, match="tokenizer.json"):
             _host.Generator(d)
+
+
+def test_continuous_batching_scheduler_matches_per_sequence_oracle():
+    """host/scheduler.*: requests of different lengths arrive over time, share ragged prefill and decode steps of the real
+    engine, finish independently -- every result must equal the CPU oracle's greedy continuation of that prompt alone."""
+    from gabby_b200 import _host
+    from oracle import pyoracle as po
+    from tests.helpers import synth_tensors, make_engine
+    arch, tensors = synth_tensors("tiny128", None, 77)
+    eng = make_engine(arch, tensors, max_batch=4, max_positions=96, page_size=16, num_pages=20, max_prefill_tokens=96)
+    om = po.OracleModel(arch, tensors, 96)
+    lens = [5, 33, 17, 1, 48, 9, 26]
+    news = [12, 6, 20, 9, 5, 16, 8]
+    prompts = [synth.synth_prompt(n, arch.vocab_size, arch.bos_token_id, 400 + i) for i, n in enumerate(lens)]
+    expect = [om.seq(po.ORC_KV_BF16).greedy(p, m)[0].tolist() for p, m in zip(prompts, news)]
+    stop_id = expect[0][2]                                   # request 0 must stop right before this token
+    want0 = expect[0][:expect[0].index(stop_id)]
+    sched = _host.Scheduler(eng, eos_ids=[stop_id], max_batch=4, max_positions=96, max_prefill_tokens=96, num_pages=20, page_size=16)
+    ids = [sched.submit(p, m) for p, m in zip(prompts[:4], news[:4])]
+    for _ in range(3):
+        sched.step()
+    ids += [sched.submit(p, m) for p, m in zip(prompts[4:], news[4:])]
+    sched.drain()
+    for i, rid in enumerate(ids):
+        toks, fin, done = sched.result(rid)
+        exp = expect[i]
+        if stop_id in exp:
+            exp = exp[:exp.index(stop_id)]
+            assert fin == "stop", (i, fin)
+        else:
+            assert fin == "length", (i, fin)
+        assert done and toks == exp, (i, toks, exp)
+    assert sched.result(ids[0])[0] == want0
+    st = sched.stats()
+    assert st["max_concurrent"] >= 3 and st["free_pages"] == 20
+    sched.close()
+    eng.close()

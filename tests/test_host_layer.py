@@ -165,3 +165,71 @@ def test_generator_load_fails_loudly_without_gpu():
             _host.Generator(d)
     with pytest.raises(_host.HostError, match="config.json"):
         _host.Generator("/nonexistent/model/dir")
+
+
+# ---- continuous batching (host/scheduler.*) over the deterministic fake engine ---------------------------------
+def _fake_sequential(prompt, max_new, vocab, eos):
+    out, last, pos = [], prompt[-1], len(prompt) - 1
+    while True:
+        nxt = (31 * last + 7 * pos + 3) % vocab
+        if nxt == eos:
+            return out, "stop"
+        out.append(nxt)
+        if len(out) >= max_new:
+            return out, "length"
+        last, pos = nxt, pos + 1
+
+
+def test_scheduler_batches_ragged_requests_and_matches_sequential_generation():
+    from gabby_b200 import _host
+    vocab, eos = 997, 13
+    rng = np.random.default_rng(3)
+    reqs = [(rng.integers(1, vocab, size=int(rng.integers(1, 60))).tolist(), int(rng.integers(1, 40))) for _ in range(23)]
+    s = _host.Scheduler(None, eos_ids=[eos], max_batch=4, max_positions=128, max_prefill_tokens=128, num_pages=64, page_size=16,
+                        fake_vocab=vocab)
+    ids = [s.submit(p, m) for p, m in reqs[:10]]
+    for _ in range(5):                      # requests keep arriving while others are running
+        s.step()
+    ids += [s.submit(p, m) for p, m in reqs[10:]]
+    s.drain()
+    for rid, (p, m) in zip(ids, reqs):
+        toks, fin, done = s.result(rid)
+        exp, exp_fin = _fake_sequential(p, m, vocab, eos)
+        assert done and toks == exp and fin == exp_fin, (rid, fin, exp_fin)
+    st = s.stats()
+    assert st["max_concurrent"] == 4                      # the batch filled up
+    assert st["decode_calls"] < sum(len(_fake_sequential(p, m, vocab, eos)[0]) for p, m in reqs)   # steps were shared
+    assert st["free_pages"] == 64                         # every page came back
+    assert st["prefill_tokens"] >= sum(len(p) for p, _ in reqs)
+    s.close()
+
+
+def test_scheduler_preempts_and_recomputes_when_the_kv_pool_runs_out():
+    from gabby_b200 import _host
+    vocab, eos = 1009, 1008   # this eos is rarely produced: sequences run to their length limit
+    # 6 pages of 16 tokens; three sequences of 20 + 40 tokens each need 4 pages apiece -> cannot all grow at once
+    s = _host.Scheduler(None, eos_ids=[eos], max_batch=3, max_positions=64, max_prefill_tokens=64, num_pages=6, page_size=16,
+                        fake_vocab=vocab)
+    prompts = [[(7 * i + j) % vocab + 1 for j in range(20)] for i in range(3)]
+    ids = [s.submit(p, 40) for p in prompts]
+    s.drain()
+    for rid, p in zip(ids, prompts):
+        toks, fin, done = s.result(rid)
+        exp, exp_fin = _fake_sequential(p, 40, vocab, eos)
+        assert done and toks == exp and fin == exp_fin
+    st = s.stats()
+    assert st["preemptions"] >= 1 and st["free_pages"] == 6
+    s.close()
+
+
+def test_scheduler_rejects_requests_that_can_never_run():
+    from gabby_b200 import _host
+    s = _host.Scheduler(None, eos_ids=[5], max_batch=2, max_positions=32, max_prefill_tokens=32, num_pages=4, page_size=16, fake_vocab=100)
+    with pytest.raises(_host.HostError):
+        s.submit([], 4)
+    with pytest.raises(_host.HostError):
+        s.submit([1] * 30, 8)          # prompt + max_new > max_positions
+    with pytest.raises(_host.HostError):
+        s.submit([1, 2, 3], 0)
+    assert s.step() == 0               # idle
+    s.close()
