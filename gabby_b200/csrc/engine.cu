@@ -12,6 +12,8 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <functional>
+#include <set>
+#include <utility>
 
 #include "decode_kernels.cuh"
 #include "mega_decode.cuh"
@@ -113,6 +115,27 @@ T* dalloc(b2l_ctx* c, size_t n) {
     return static_cast<T*>(p);
 }
 
+// The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: remember which
+// (kernel, device) pairs have it, so that a context on a second GPU of the same process gets it too.
+void ensure_smem_optin(const void* kern, int device, size_t bytes) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({kern, device})) return;
+    B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    done.insert({kern, device});
+}
+
+// The megakernel's launch arguments live in one __constant__ symbol per device (mega_decode.cuh: c_mega) and the
+// persistent kernel reads them for as long as it runs: contexts that share a GPU take this lock from the argument
+// upload until their launch has finished (the kernel occupies every SM anyway, so nothing is lost).
+std::mutex& mega_device_mutex(int device) {
+    static std::mutex table_mu;
+    static std::map<int, std::mutex> per_device;
+    std::lock_guard<std::mutex> lock(table_mu);
+    return per_device[device];
+}
+
 Placement place_tensor(b2l_ctx* c, Kind k, int layer, const int64_t* shape, int ndim) {
     const b2l_params& p = c->p;
     const int64_t H = c->H, r = p.tp_rank;
@@ -181,12 +204,8 @@ int gemv_kt(int B, int K) {
 
 template <int B, int MODE, bool NORM>
 void gemv_launch_b(b2l_ctx* c, const GemvArgs& a) {
-    static bool configured = false;
     auto kern = gemv_kernel<B, MODE, NORM>;
-    if (!configured) {
-        B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemvSmemBudget)));
-        configured = true;
-    }
+    ensure_smem_optin(reinterpret_cast<const void*>(kern), c->p.device, kGemvSmemBudget);
     const int n_blocks = (a.N + kGemvRowsPerCta - 1) / kGemvRowsPerCta;
     const int grid = std::min(n_blocks, c->prop.multiProcessorCount * 8);
     launch(c, kern, dim3(grid), dim3(kGemvThreads), static_cast<size_t>(B) * a.kt * sizeof(float), a);
@@ -249,11 +268,7 @@ void attn_launch_hd(b2l_ctx* c, const AttnArgs& a, int R) {
         if (use_mma) {   // tensor-core kernel (attn_decode_mma.cuh); B2L_ATTN_MMA=0 selects the CUDA-core kernel
             constexpr size_t smem = attn_mma_smem<HD>();
             auto go = [&](auto kern) {
-                static bool configured = false;
-                if (!configured) {
-                    B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                    configured = true;
-                }
+                ensure_smem_optin(reinterpret_cast<const void*>(kern), c->p.device, smem);
                 launch(c, kern, grid, block, smem, a);
             };
             switch (c->group) {
@@ -573,12 +588,8 @@ void prefill_gemm(b2l_ctx* c, int T, int n_seq, int tap_row0) {
             const dim3 grid(c->pf_n_tiles, c->nh_l);
             // shared memory: the Q tile + two {K, V} buffers of 64 padded rows each
             const size_t fsmem = static_cast<size_t>(5) * 64 * (c->hd + 8) * 2;
-            static bool configured = false;
-            if (!configured) {
-                B2L_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * (64 + 8) * 2));
-                B2L_CUDA(cudaFuncSetAttribute(flash_prefill_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * 64 * (128 + 8) * 2));
-                configured = true;
-            }
+            ensure_smem_optin(reinterpret_cast<const void*>(flash_prefill_kernel<64>), c->p.device, 5 * 64 * (64 + 8) * 2);
+            ensure_smem_optin(reinterpret_cast<const void*>(flash_prefill_kernel<128>), c->p.device, 5 * 64 * (128 + 8) * 2);
             if (c->hd == 64) flash_prefill_kernel<64><<<grid, kFlashThreads, fsmem, c->stream>>>(fa);
             else flash_prefill_kernel<128><<<grid, kFlashThreads, fsmem, c->stream>>>(fa);
             B2L_CUDA(cudaGetLastError());
@@ -936,11 +947,7 @@ void gemm_bf16(b2l_ctx* c, const uint16_t* A, const uint16_t* W, GemmArgs g) {
     constexpr int BN = 128;
     const CUtensorMap ma = make_kmajor_map(A, g.M, g.K, kGemmBM), mw = make_kmajor_map(W, g.N, g.K, BN);
     const size_t smem = static_cast<size_t>(kGemmStages) * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 16 * kGemmStages + 64 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        B2L_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
-    }
+    ensure_smem_optin(reinterpret_cast<const void*>(gemm_bf16_tcgen05_kernel<BN>), c->p.device, smem);
     const dim3 grid(g.N / BN, (g.M + kGemmBM - 1) / kGemmBM);
     gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, smem, c->stream>>>(ma, mw, g);
     B2L_CUDA(cudaGetLastError());
@@ -1047,6 +1054,7 @@ int b2l_create(const b2l_params* p, const float* rope_cos_sin, const void* nccl_
         const size_t page_elems = static_cast<size_t>(2) * p->page_size * c->kvd_l;
         // one allocation for every layer's KV pool: lets one L2 persisting window cover the whole cache
         c->kv_base = dalloc<uint16_t>(c, page_elems * p->num_pages * c->L);
+        B2L_CUDA(cudaMemset(c->kv_base, 0, sizeof(uint16_t) * page_elems * p->num_pages * c->L));   // timing runs decode over pages nobody prefilled
         size_t kv_off = 0;
         for (auto& w : c->layers) {
             w.in_norm = dalloc<uint16_t>(c, H);
@@ -1245,8 +1253,11 @@ int b2l_decode(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* posi
             io[0] = tokens[0];
             io[1] = positions[0];
             io[2] = -1;
-            mega_enqueue(c, 1, true);
-            mega_check(c, cudaStreamSynchronize(c->stream));
+            {
+                std::lock_guard<std::mutex> dev_lock(mega_device_mutex(c->p.device));
+                mega_enqueue(c, 1, true);
+                mega_check(c, cudaStreamSynchronize(c->stream));
+            }
             B2L_CHECK(io[2] >= 0, "megakernel returned no token");
             next_ids[0] = io[2];
         } else {
@@ -1289,9 +1300,12 @@ int b2l_decode_loop(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t*
         upload_block_tables(c, n_seq, block_tables, max_blocks, need.data());
         const bool mega = c->decode_mode == 1 && n_seq == 1;
         if (mega) {
+            std::lock_guard<std::mutex> dev_lock(mega_device_mutex(c->p.device));
             B2L_CUDA(cudaEventRecord(c->ev0, c->stream));
             mega_enqueue(c, n_steps);
             B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
+            mega_check(c, cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
+            mega_check(c, cudaStreamSynchronize(c->stream));
         } else {
             B2L_CUDA(cudaMemsetAsync(c->d_step, 0, sizeof(int32_t), c->stream));
             Graph& g = decode_graph(c, n_seq, true);
@@ -1300,10 +1314,7 @@ int b2l_decode_loop(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t*
             B2L_CUDA(cudaEventRecord(c->ev1, c->stream));
             c->launched += static_cast<int64_t>(g.nodes) * n_steps;
         }
-        if (mega) {
-            mega_check(c, cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
-            mega_check(c, cudaStreamSynchronize(c->stream));
-        } else {
+        if (!mega) {
             B2L_CUDA(cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * n_steps * n_seq, cudaMemcpyDeviceToHost, c->stream));
             B2L_CUDA(cudaStreamSynchronize(c->stream));
         }

@@ -34,8 +34,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  "l"(map), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
 }
+// bounded: a bad tensor map or a lost TMA transaction traps (the launch fails with an error) instead of hanging the GPU.
+// try_wait suspends the thread for a hardware-defined interval per attempt, so 2^26 attempts is tens of seconds.
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
