@@ -378,7 +378,7 @@ def measure_3b_b8(local: int, K: int, W: int):
         "workload": "llama-3.2-3b bf16 batch 8: 2048-token prefill + greedy decode (BASELINE configs[2])", "batch": B, "context": [S, S + K],
         "steps": K, "warmup": W,
         "decode": {"tok_per_s": B * 1000.0 / ms_per_step, "ms_per_step": ms_per_step, "GBps": achieved, "peak_GBps": peak, "frac": achieved / peak,
-                   "hbm_bytes_per_step": bytes_per_step, "kernels_per_step": launches // K, "e2e_tok_per_s": e2e, "decode_mode": mode,
+                   "hbm_bytes_per_step": bytes_per_step, "kernels_per_step": launches // K, "e2e_tok_per_s": e2e, "decode_mode": 0 if B > 1 else mode,   # the megakernel is batch 1 only
                    "h2d_bytes_per_step": B * (12 + 4 * eng.max_blocks), "d2h_bytes_per_step": 4 * B},
         "prefill": {"tokens": B * S, "seconds": pf_s, "tok_per_s": B * S / pf_s, "algorithmic_tflop": flops / 1e12,
                     "achieved_tflops": flops / pf_s / 1e12, "peak_tflops": tf_peak, "frac": flops / pf_s / 1e12 / tf_peak, "bound": "tensor",

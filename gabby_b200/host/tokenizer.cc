@@ -32,38 +32,113 @@ std::vector<std::string> Utf8Chars(const std::string& s) {
     return out;
 }
 
-enum CharClass { kSpace, kLetter, kDigit, kOther };
-CharClass Classify(unsigned char c) {
-    if (c == ' ' || c == '\t' || c == '\n' || c == '\r') return kSpace;
-    if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80) return kLetter;  // non-ASCII bytes group with letters
-    if (c >= '0' && c <= '9') return kDigit;
-    return kOther;
+#include "unicode_tables.inc"
+
+template <size_t N>
+bool InRanges(const uint32_t (&r)[N][2], uint32_t cp) {
+    size_t lo = 0, hi = N;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) / 2;
+        if (cp < r[mid][0]) hi = mid;
+        else if (cp > r[mid][1]) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+bool IsLetter(uint32_t c) { return c < 0x80 ? ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') : InRanges(kUnicodeLetter, c); }
+bool IsNumber(uint32_t c) { return c < 0x80 ? (c >= '0' && c <= '9') : InRanges(kUnicodeNumber, c); }
+bool IsSpace(uint32_t c) { return c < 0x80 ? (c == ' ' || (c >= 0x9 && c <= 0xD)) : InRanges(kUnicodeSpace, c); }
+bool IsNewline(uint32_t c) { return c == '\r' || c == '\n'; }
+
+// UTF-8 -> code points with the byte offset of each (malformed bytes become one code point each, so that every
+// input byte is covered and the byte-level BPE below still sees it)
+void DecodeUtf8(std::string_view s, std::vector<uint32_t>& cps, std::vector<size_t>& offs) {
+    for (size_t i = 0; i < s.size();) {
+        const unsigned char c = static_cast<unsigned char>(s[i]);
+        size_t n = c < 0x80 ? 1 : (c >> 5) == 6 ? 2 : (c >> 4) == 14 ? 3 : (c >> 3) == 30 ? 4 : 1;
+        if (i + n > s.size()) n = 1;
+        uint32_t cp = c;
+        if (n > 1) {
+            cp = c & (0xFF >> (n + 1));
+            for (size_t k = 1; k < n; k++) {
+                const unsigned char cc = static_cast<unsigned char>(s[i + k]);
+                if ((cc & 0xC0) != 0x80) { n = 1; cp = c; break; }
+                cp = (cp << 6) | (cc & 0x3F);
+            }
+        }
+        if (n == 1 && c >= 0x80) cp = 0xFFFD;   // stray byte: not a letter, number or space
+        cps.push_back(cp);
+        offs.push_back(i);
+        i += n;
+    }
+    offs.push_back(s.size());
 }
 
-// Approximation of the Llama-3 pre-tokenizer regex: an optional single leading space glued to a run of
-// letters / a run of punctuation, digits in groups of <= 3, whitespace runs kept together.
+// The Llama-3 pre-tokenizer (tokenizer.json: pre_tokenizer.pretokenizers[0], Split / Isolated):
+//   (?i:'s|'t|'re|'ve|'m|'ll|'d) | [^\r\n\p{L}\p{N}]?\p{L}+ | \p{N}{1,3} | ' '?[^\s\p{L}\p{N}]+[\r\n]* | \s*[\r\n]+ | \s+(?!\S) | \s+
+// matched leftmost-first, alternatives in this order, each greedy with backtracking -- written out by hand over code points.
 std::vector<std::string> PreTokenize(std::string_view s) {
+    std::vector<uint32_t> c;
+    std::vector<size_t> off;
+    DecodeUtf8(s, c, off);
+    const size_t n = c.size();
     std::vector<std::string> out;
+    auto lower = [](uint32_t x) { return x >= 'A' && x <= 'Z' ? x + 32 : x; };
     size_t i = 0;
-    while (i < s.size()) {
-        size_t start = i;
-        unsigned char c = static_cast<unsigned char>(s[i]);
-        if (c == ' ' && i + 1 < s.size() && Classify(static_cast<unsigned char>(s[i + 1])) != kSpace) {
-            i++;  // the space travels with the following word
-            c = static_cast<unsigned char>(s[i]);
+    while (i < n) {
+        size_t end = 0;
+        // 1. contractions, case-insensitive
+        if (c[i] == '\'' && i + 1 < n) {
+            const uint32_t a = lower(c[i + 1]), b = i + 2 < n ? lower(c[i + 2]) : 0;
+            if (a == 's' || a == 't') end = i + 2;
+            else if ((a == 'r' && b == 'e') || (a == 'v' && b == 'e')) end = i + 3;
+            else if (a == 'm') end = i + 2;
+            else if (a == 'l' && b == 'l') end = i + 3;
+            else if (a == 'd') end = i + 2;
         }
-        const CharClass cls = Classify(c);
-        if (cls == kDigit) {
-            size_t n = 0;
-            while (i < s.size() && Classify(static_cast<unsigned char>(s[i])) == kDigit && n < 3) i++, n++;
-        } else if (cls == kSpace) {
-            while (i < s.size() && Classify(static_cast<unsigned char>(s[i])) == kSpace) i++;
-            // leave the last space for the next word when one follows
-            if (i < s.size() && i - start > 1 && s[i - 1] == ' ') i--;
-        } else {
-            while (i < s.size() && Classify(static_cast<unsigned char>(s[i])) == cls) i++;
+        // 2. an optional non-letter/number/newline character, then letters
+        if (!end) {
+            size_t j = i;
+            if (!IsNewline(c[j]) && !IsLetter(c[j]) && !IsNumber(c[j]) && j + 1 < n && IsLetter(c[j + 1])) j++;
+            if (IsLetter(c[j])) {
+                while (j < n && IsLetter(c[j])) j++;
+                end = j;
+            }
         }
-        out.emplace_back(s.substr(start, i - start));
+        // 3. one to three numbers
+        if (!end && IsNumber(c[i])) {
+            size_t j = i;
+            while (j < n && j < i + 3 && IsNumber(c[j])) j++;
+            end = j;
+        }
+        // 4. an optional space, then characters that are neither space, letter nor number, then newlines
+        if (!end) {
+            size_t j = i;
+            auto other = [&](size_t k) { return k < n && !IsSpace(c[k]) && !IsLetter(c[k]) && !IsNumber(c[k]); };
+            if (c[j] == ' ' && other(j + 1)) j++;
+            if (other(j)) {
+                while (other(j)) j++;
+                while (j < n && IsNewline(c[j])) j++;
+                end = j;
+            }
+        }
+        if (!end) {   // c[i] is whitespace from here on
+            size_t run = i;
+            while (run < n && IsSpace(c[run])) run++;
+            // 5. whitespace up to and including its last newline
+            size_t last_nl = 0;
+            bool have_nl = false;
+            for (size_t k = i; k < run; k++)
+                if (IsNewline(c[k])) last_nl = k, have_nl = true;
+            if (have_nl) end = last_nl + 1;
+            // 6. whitespace not followed by a non-space: everything at the end of the text, else all but the last one
+            else if (run == n) end = run;
+            else if (run - i >= 2) end = run - 1;
+            // 7. whitespace
+            else end = run;
+        }
+        out.emplace_back(s.substr(off[i], off[end] - off[i]));
+        i = end;
     }
     return out;
 }
@@ -100,6 +175,7 @@ Tokenizer::Tokenizer(json::ValuePtr, json::ValuePtr, json::ValuePtr tokens) {
                 id_to_token_[i] = tok;
             }
         }
+        if (model.contains("ignore_merges") && model.at("ignore_merges").is(json::Type::BOOL)) ignore_merges_ = model.at("ignore_merges").as_boolean();
         if (model.contains("merges") && model.at("merges").is(json::Type::ARRAY)) {
             int rank = 0;
             for (const auto& m : model.at("merges").as_array()) {
@@ -159,12 +235,38 @@ std::vector<int> Tokenizer::Tokenize(const std::string_view input) {
         for (unsigned char c : input) out.push_back(c);   // byte fallback (no vocabulary in tokenizer.json)
         return out;
     }
-    for (const std::string& word : PreTokenize(input)) {
-        std::string mapped;
-        for (unsigned char c : word) mapped += byte_to_unicode_[c];
-        const std::vector<int> ids = BpeWord(mapped);
-        out.insert(out.end(), ids.begin(), ids.end());
+    auto encode_text = [&](std::string_view text) {
+        for (const std::string& word : PreTokenize(text)) {
+            std::string mapped;
+            for (unsigned char c : word) mapped += byte_to_unicode_[c];
+            if (ignore_merges_) {   // Llama-3's tokenizer.json: a pre-token that is itself in the vocabulary is one token
+                auto it = vocab_.find(mapped);
+                if (it != vocab_.end()) {
+                    out.push_back(it->second);
+                    continue;
+                }
+            }
+            const std::vector<int> ids = BpeWord(mapped);
+            out.insert(out.end(), ids.begin(), ids.end());
+        }
+    };
+    // added (special) tokens are cut out of the raw text first: leftmost occurrence, longest content on ties
+    size_t pos = 0;
+    while (pos < input.size()) {
+        size_t best_at = std::string_view::npos, best_len = 0;
+        int best_id = -1;
+        for (const auto& [content, id] : specials_) {
+            if (content.empty()) continue;
+            const size_t at = input.find(content, pos);
+            if (at == std::string_view::npos) continue;
+            if (at < best_at || (at == best_at && content.size() > best_len)) best_at = at, best_len = content.size(), best_id = id;
+        }
+        if (best_id < 0) break;
+        if (best_at > pos) encode_text(input.substr(pos, best_at - pos));
+        out.push_back(best_id);
+        pos = best_at + best_len;
     }
+    if (pos < input.size()) encode_text(input.substr(pos));
     return out;
 }
 

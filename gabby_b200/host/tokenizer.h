@@ -3,7 +3,9 @@
 // whose reference body returns {} (tokenizer.cc:6-8). This one implements byte-level BPE from
 // tokenizer.json (model.vocab + model.merges, added_tokens as specials) with a byte fallback when the
 // file carries no vocabulary (synthetic test directories), plus the Llama-3 chat template and the
-// inverse mapping. SURVEY.md section 8(f) row 1.
+// inverse mapping. The pre-tokenizer is the Llama-3 split regex (contractions, [^\r\n\p{L}\p{N}]?\p{L}+, \p{N}{1,3},
+// punctuation runs, the whitespace alternations) over Unicode general categories (unicode_tables.inc); added tokens are
+// cut out of the text before it. SURVEY.md section 8(f) row 1.
 #pragma once
 #include <cstdint>
 #include <map>
@@ -37,6 +39,7 @@ private:
     std::vector<std::string> id_to_token_;
     std::unordered_map<std::string, int> merge_rank_;     // "a b" -> rank
     std::map<std::string, int> specials_;
+    bool ignore_merges_ = false;                          // model.ignore_merges (true in Llama-3's tokenizer.json)
     std::string byte_to_unicode_[256];
     std::unordered_map<std::string, uint8_t> unicode_to_byte_;
 };

@@ -40,6 +40,19 @@ def _engine(arch, seed, **kw):
     return make_engine(arch, None, synth_seed=seed, **kw)
 
 
+def healthy_prompt(om, n, vocab, bos, seed, n_new, min_margin=0.01):
+    """A seeded prompt whose oracle greedy continuation has top-1 margins >= min_margin at every compared step, so that
+    "bit-identical ids" is a fair demand of an implementation that sums in another order (random-init models produce
+    near-ties now and then; the seed is bumped deterministically until there is none)."""
+    po = _po()
+    for bump in range(50):
+        prompt = synth.synth_prompt(n, vocab, bos, seed + 1000 * bump)
+        oids, margins = om.seq(po.ORC_KV_BF16).greedy(prompt, n_new)
+        if float(margins.min()) >= min_margin:
+            return prompt, oids, margins
+    raise AssertionError("no prompt with healthy margins found")
+
+
 def _greedy_check(got, oids, margins, what, tie=0.0):
     """ids must be identical; with tie > 0 a divergence is tolerated only AT a step whose oracle top-1 margin is below `tie`."""
     got, oids = list(map(int, got)), list(map(int, oids))
@@ -56,12 +69,11 @@ def test_wide_prefill_and_decode_match_oracle(preset, seed):
     (3B: megakernel ks=2/m=6 and ks=4/m=8 + multi-kernel GEMV; 70B: multi-kernel only, K = 28672)."""
     po = _po()
     arch, tensors = wide_model(preset, 2, seed)
-    prompt = synth.synth_prompt(19, arch.vocab_size, arch.bos_token_id, seed + 1)
     n_new = 10
     om = po.OracleModel(arch, tensors, 64)
+    prompt, oids, margins = healthy_prompt(om, 19, arch.vocab_size, arch.bos_token_id, seed + 1, n_new + 1)
     s = om.seq(po.ORC_KV_BF16)
     ologits, ohidden = s.forward(prompt, want_hidden=True)
-    oids, margins = om.seq(po.ORC_KV_BF16).greedy(prompt, n_new + 1)
     s2 = om.seq(po.ORC_KV_BF16)
     olast, _ = s2.forward(np.concatenate([prompt, oids[:n_new]]).astype(np.int32))
     modes_run = []
@@ -97,22 +109,21 @@ def test_wide_batched_decode_on_tensor_cores_matches_oracle(preset, seed, n_seq)
     po = _po()
     arch, tensors = wide_model(preset, 2, seed)
     lens = [(5 * i + 3) % 24 + 1 for i in range(n_seq)]
-    prompts = [synth.synth_prompt(n, arch.vocab_size, arch.bos_token_id, 500 + i) for i, n in enumerate(lens)]
+    n_new = 5
+    om = po.OracleModel(arch, tensors, 48)
+    picked = [healthy_prompt(om, n, arch.vocab_size, arch.bos_token_id, 500 + i, n_new + 1) for i, n in enumerate(lens)]
+    prompts = [p for p, _, _ in picked]
     eng = _engine(arch, seed, max_batch=n_seq, max_positions=48, max_prefill_tokens=32 * n_seq)
     assert eng.info().batched_tensor_core == 1
     eng.set_prefill_mode(0)
     bt = contiguous_tables(n_seq, eng.max_blocks)
     first = eng.prefill(prompts, [0] * n_seq, bt)
-    n_new = 5
     ids, _ = eng.decode_loop(first, lens, bt, n_new)
     last_logits = eng.logits(0, n_seq).copy()
     eng.close()
-    om = po.OracleModel(arch, tensors, 48)
-    for i, p in enumerate(prompts):
+    for i, (p, oids, margins) in enumerate(picked):
         seq = om.seq(po.ORC_KV_BF16)
-        oids, margins = seq.greedy(p, n_new + 1)
         _greedy_check([first[i]] + ids[:, i].tolist(), oids, margins, f"{preset} seq {i}")
-        seq.reset()
         ol, _ = seq.forward(np.concatenate([p, oids[:n_new]]).astype(np.int32))
         assert np.abs(last_logits[i] - ol[0]).max() < 5e-3, (i, float(np.abs(last_logits[i] - ol[0]).max()))
 

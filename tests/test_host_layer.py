@@ -143,6 +143,54 @@ def test_tokenizer_reference_contract_and_bpe_against_hf_tokenizers():
     assert ids[0] == hf.token_to_id("<|begin_of_text|>") and ids.count(hf.token_to_id("<|eot_id|>")) == 2
 
 
+LLAMA3_SPLIT = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+")
+
+
+def _llama3_style_tokenizer():
+    """A byte-level BPE trained here, configured exactly like Llama-3's tokenizer.json: Split(regex, isolated) +
+    ByteLevel(use_regex=False), ignore_merges, special tokens as added tokens."""
+    from tokenizers import Regex, Tokenizer as HfTok, decoders, models, pre_tokenizers, trainers
+    hf = HfTok(models.BPE(ignore_merges=True))
+    hf.pre_tokenizer = pre_tokenizers.Sequence([
+        pre_tokenizers.Split(Regex(LLAMA3_SPLIT), behavior="isolated", invert=False),
+        pre_tokenizers.ByteLevel(add_prefix_space=False, trim_offsets=True, use_regex=False)])
+    hf.decoder = decoders.ByteLevel()
+    corpus = ["The quick brown fox doesn't jump over 12345 lazy dogs!", "I'll say: we've been here, haven't we?  Yes.",
+              "naïve café über straße", "日本語のテキストと中文文本", "prices: $1,234.56 or 99% off...", "tabs\tand\nnewlines\r\n  spaces   ",
+              "emoji 🙂🙂 and ünïcödé", "HE'S SHOUTING AND SHE'LL HEAR", "x = y**2 + 3*z; // comment"] * 30
+    hf.train_from_iterator(corpus, trainers.BpeTrainer(
+        vocab_size=600, special_tokens=["<|begin_of_text|>", "<|start_header_id|>", "<|end_header_id|>", "<|eot_id|>"],
+        initial_alphabet=pre_tokenizers.ByteLevel.alphabet()))
+    return hf
+
+
+def test_tokenizer_llama3_pretokenizer_matches_hf_tokenizers_on_unicode_digits_contractions_whitespace():
+    """SURVEY.md section 8(f) row 1 / the reference's next TODO (tokenizer.cc:6-11): ids must equal what HF `tokenizers` produces
+    with Llama-3's own pre-tokenizer configuration."""
+    pytest.importorskip("tokenizers")
+    hf = _llama3_style_tokenizer()
+    ours = _host.Tokenizer(hf.to_str())
+    texts = [
+        "Hello world", " 123", "12345678", "a 1234 b", "I'll we've doesn't he'd I'm you're IT'S O'Reilly",
+        "don't  stop", "x  y   z", "trailing   ", "  leading", "line1\nline2", "a\n\n\nb", "a \n b", "tab\there", "crlf\r\nnext",
+        "   \n   x", "wow!!!\n\nnext", "a.b,c;d", " ...!?", "$1,234.56", "99% off", "naïve café", "über straße", "Ünïcödé",
+        "日本語のテキスト", "中文 文本 123", "emoji 🙂🙂!", "mixed日本123abc", "ǅ Ⅻ ² ½", "\u00a0nbsp\u2003emspace", "don't<|eot_id|>stop",
+        "<|begin_of_text|>hi<|eot_id|>", "a<|start_header_id|>user<|end_header_id|>\n\nhey", "'", "''s", "'S", " 's", "1 2 3",
+        "x\u2028y", "snake_case_name __init__", "C++ && C#", "http://example.com/a?b=c&d=1", "",
+    ]
+    for text in texts:
+        want = hf.encode(text, add_special_tokens=False).ids
+        got = ours.tokenize(text)
+        assert got == want, (text, got, want, [hf.id_to_token(i) for i in want])
+    rng = np.random.default_rng(7)
+    alphabet = list("abcXYZ 019'\n\t.,!-_é日本🙂 \r") + ["'s", "'ll", "  ", "<|eot_id|>"]
+    for _ in range(300):
+        text = "".join(rng.choice(alphabet, size=int(rng.integers(1, 24))))
+        assert ours.tokenize(text) == hf.encode(text, add_special_tokens=False).ids, repr(text)
+    for text in ["I'll say: we've been here", "日本語 and café 🙂", "  spaces\n\nand\ttabs  "]:
+        assert ours.detokenize(ours.tokenize(text)) == text
+
+
 def test_host_argmax_first_max():
     assert _host.argmax([1.0, 3.0, 3.0, -1.0]) == 1
     assert _host.argmax([-np.inf, -np.inf]) == 0

@@ -136,3 +136,25 @@ def test_loading_through_reference_parsers_gives_same_logits():
         assert buf.value == b"hey this is gabby, how are u"
         r.orc_ref_free(h)
         mr.close()
+
+
+def test_bench_parity_golden_ids_are_what_the_oracle_produces():
+    """tests/golden/bench_parity.json (read by bench.py's parity_check legs) is regenerated here for its shortest leg and
+    compared, so that the committed ids cannot drift from the oracle (generator: tests/golden/make_bench_parity.py)."""
+    import importlib.util
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_bench_parity", os.path.join(path, "make_bench_parity.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    with open(os.path.join(path, "bench_parity.json")) as f:
+        gold = json.load(f)
+    assert gold["seed"] == mk.SEED
+    leg = gold["legs"]["8b_l2"]
+    arch, tensors = mk.model(leg["preset"])
+    om = po.OracleModel(arch, tensors, 100)
+    for i, (n, sd) in enumerate(zip(leg["prompt_lens"], leg["prompt_seeds"])):
+        prompt = synth.synth_prompt(n, arch.vocab_size, arch.bos_token_id, sd)
+        ids, margins = mk.greedy(om, prompt, len(leg["ids"][i]), po.ORC_KV_BF16)
+        assert ids == leg["ids"][i]
+        assert np.allclose(margins, leg["margins"][i], atol=1e-5)
