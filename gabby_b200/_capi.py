@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("B2L_LIB_PATH", LIB_PATH)   # development builds (prof
 
 # every symbol include/b2l.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
-    "b2l_create", "b2l_nccl_unique_id", "b2l_shard_window", "b2l_upload_tensor", "b2l_synth_tensor", "b2l_finalize", "b2l_destroy",
+    "b2l_create", "b2l_nccl_unique_id", "b2l_shard_window", "b2l_is_model_tensor", "b2l_upload_tensor", "b2l_synth_tensor", "b2l_finalize", "b2l_destroy",
     "b2l_prefill", "b2l_decode", "b2l_decode_loop", "b2l_get_logits", "b2l_set_taps", "b2l_get_hidden",
     "b2l_get_kv_page", "b2l_get_info", "b2l_set_decode_mode", "b2l_set_prefill_mode", "b2l_debug_mega_profile", "b2l_last_error", "b2l_op_gemv", "b2l_op_argmax", "b2l_op_gemm_bf16",
 ]
@@ -62,6 +62,8 @@ def lib():
     L.b2l_upload_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_int64), C.c_int]
     L.b2l_synth_tensor.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64), C.c_int, C.c_uint32, C.c_float, C.c_float]
     L.b2l_shard_window.argtypes = [C.POINTER(B2lParams), C.c_char_p, C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int64)]
+    if hasattr(L, "b2l_is_model_tensor"):   # absent from older development builds selected with B2L_LIB_PATH
+        L.b2l_is_model_tensor.argtypes = [C.c_char_p]
     L.b2l_finalize.argtypes = [vp]
     L.b2l_destroy.argtypes = [vp]
     L.b2l_destroy.restype = None

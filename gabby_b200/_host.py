@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(PKG, "libgabby_host.so")
 
 SYMBOLS = [
     "gb_last_error", "gb_rope_table", "gb_generator_load", "gb_generator_free", "gb_generator_generate",
-    "gb_generator_generate_ids", "gb_generator_engine", "gb_params_from_dir", "gb_params_from_json",
+    "gb_generator_generate_detailed", "gb_generator_generate_ids", "gb_generator_sched_stats", "gb_generator_engine", "gb_params_from_dir", "gb_params_from_json",
     "gb_checkpoint_info", "gb_checkpoint_tensor", "gb_kv_create", "gb_kv_free", "gb_kv_new_sequence", "gb_kv_reserve",
     "gb_kv_release", "gb_kv_table", "gb_kv_free_pages", "gb_tokenizer_create", "gb_tokenizer_free", "gb_tokenize",
     "gb_detokenize", "gb_chat_prompt", "gb_argmax",
@@ -52,7 +52,9 @@ def lib():
         L.gb_generator_free.argtypes = [vp]
         L.gb_generator_free.restype = None
         L.gb_generator_generate.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
-        L.gb_generator_generate_ids.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, ip, ip]
+        L.gb_generator_generate_detailed.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int, ip, ip, ip]
+        L.gb_generator_generate_ids.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, ip, ip]
+        L.gb_generator_sched_stats.argtypes = [vp, vp]
         L.gb_generator_engine.argtypes = [vp]
         L.gb_generator_engine.restype = vp
         L.gb_params_from_dir.argtypes = [C.c_char_p, C.POINTER(GbParams)]
@@ -208,8 +210,20 @@ class Generator:
         out = np.zeros(max_new_tokens + 1, np.int32)
         n, fin = C.c_int(0), C.c_int(0)
         _ck(lib().gb_generator_generate_ids(self.h, p.ctypes.data_as(C.c_void_p), p.size, max_new_tokens, int(device_loop),
-                                            out.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(fin)))
-        return out[: n.value].copy(), {1: "stop", 2: "length"}.get(fin.value, "none")
+                                            out.ctypes.data_as(C.c_void_p), out.size, C.byref(n), C.byref(fin)))
+        return out[: min(n.value, out.size)].copy(), {1: "stop", 2: "length"}.get(fin.value, "none")
+
+    def generate_detailed(self, system: str, user: str, max_tokens: int = 0, cap: int = 1 << 16):
+        """-> (text, prompt_tokens, completion_tokens, finish_reason): what an OpenAI-style response reports."""
+        buf = C.create_string_buffer(cap)
+        pt, ct, fin = C.c_int(0), C.c_int(0), C.c_int(0)
+        _ck(lib().gb_generator_generate_detailed(self.h, system.encode(), user.encode(), max_tokens, buf, cap, C.byref(pt), C.byref(ct), C.byref(fin)))
+        return buf.value.decode(errors="replace"), pt.value, ct.value, {1: "stop", 2: "length"}.get(fin.value, "none")
+
+    def sched_stats(self):
+        out = np.zeros(8, np.int64)
+        _ck(lib().gb_generator_sched_stats(self.h, out.ctypes.data_as(C.c_void_p)))
+        return dict(zip(["steps", "prefill_calls", "decode_calls", "prefill_tokens", "decode_tokens", "preemptions", "max_concurrent", "free_pages"], out.tolist()))
 
     def close(self):
         if getattr(self, "h", None):

@@ -48,7 +48,10 @@ def build_host(force: bool = False) -> str | None:
     out = os.path.join(PKG, "libgabby_host.so")
     deps = glob.glob(os.path.join(hdir, "*")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
     if force or _newer(out, deps):
-        cmd = [CXX, "-O2", "-std=c++20", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + hdir,
+        # hidden visibility + -Bsymbolic: only the gb_* entry points (GB_API) are exported and the library's own references
+        # bind inside it, so it can be linked next to gabby's gabby::inference:: / gabby::json:: symbols (integration/)
+        cmd = [CXX, "-O2", "-std=c++20", "-fPIC", "-shared", "-Wall", "-fvisibility=hidden", "-fvisibility-inlines-hidden",
+               "-Wl,-Bsymbolic", "-I" + os.path.join(ROOT, "include"), "-I" + hdir,
                "-o", out] + srcs + ["-L" + PKG, "-lb2l", "-Wl,-rpath,$ORIGIN", "-lpthread"]
         subprocess.run(cmd, check=True)
     return out

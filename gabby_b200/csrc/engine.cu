@@ -16,7 +16,18 @@
 #include <utility>
 
 #include "decode_kernels.cuh"
+#include "mega_common.cuh"
+// the decode megakernel is compiled twice from one source: the single-GPU kernel and the kernel of a tensor-parallel rank
+#define MEGA_TP 0
+#define MEGA_NS mega1
 #include "mega_decode.cuh"
+#undef MEGA_TP
+#undef MEGA_NS
+#define MEGA_TP 1
+#define MEGA_NS megatp
+#include "mega_decode.cuh"
+#undef MEGA_TP
+#undef MEGA_NS
 #include "gemm_tcgen05.cuh"
 #include "flash_prefill.cuh"
 #include "skinny_gemm.cuh"
@@ -392,7 +403,12 @@ void tp_peer_setup(b2l_ctx* c) {
     const int tp = c->p.tp_size, rank = c->p.tp_rank;
     const char* env = std::getenv("B2L_TP_TRANSPORT");
     const bool want = !(env && std::string(env) == "nccl") && tp <= kTpMaxRanks;
-    const size_t words = static_cast<size_t>(2) * tp * c->max_rows * c->H;
+    // [multi-kernel path: 2 slots x tp x max_rows x H] [megakernel: 2 phases x tp x H] [megakernel argmax keys: tp x 2 x SMs]
+    // (the two decode paths number their sequences independently, so they must not share words)
+    const size_t mk_words = static_cast<size_t>(2) * tp * c->max_rows * c->H;
+    c->tp_mega_off = mk_words;
+    c->tp_keys_off = mk_words + static_cast<size_t>(2) * tp * c->H;
+    const size_t words = c->tp_keys_off + static_cast<size_t>(tp) * 2 * c->prop.multiProcessorCount;
     c->tp_ll = dalloc<uint2>(c, words);
     B2L_CUDA(cudaMemset(c->tp_ll, 0, words * sizeof(uint2)));      // sequence 0 is never sent
     c->tp_seq = dalloc<uint32_t>(c, 2);
@@ -710,7 +726,7 @@ bool mega_shape(int K, int* ks, int* m) {
 void mega_setup(b2l_ctx* c) {
     c->mega_ok = false;
     auto no = [&](const std::string& why) { c->mega_why = why; };
-    if (c->p.tp_size != 1) return no("tensor-parallel ranks use the multi-kernel path");
+    if (c->p.tp_size != 1 && !c->tp_peer_ok) return no("tensor-parallel megakernel needs the NVLink peer-memory transport");
     const int G = c->prop.multiProcessorCount;
     std::vector<MegaPhase> ph;
     auto add = [&](int type, int layer, const uint16_t* W, const uint16_t* norm, uint16_t* kv, int N, int K) -> bool {
@@ -731,7 +747,15 @@ void mega_setup(b2l_ctx* c) {
         ok = ok && add(PH_DOWN, l, w.w_down, nullptr, nullptr, c->H, c->I_l);
     }
     ok = ok && add(PH_LMHEAD, c->L, c->lm_head, c->final_norm, nullptr, c->V_l, c->H);
-    if (!ok) return no("a weight matrix has K that is not 256*m*ks with m<=8, ks in {1,2,4,8}");
+    if (!ok) return no("a weight matrix has K that is not 256*m*ks with m<=8, ks in {1,2,4}");
+    if (c->p.tp_size > 1) {
+        // the row-parallel phases collect their tp partial sums in a second pass that is unrolled over <= 4 rounds of rows
+        for (const MegaPhase& p : ph) {
+            if (p.type != PH_OPROJ && p.type != PH_DOWN) continue;
+            const int rows_per_cta = (p.N + G - 1) / G, rows_per_round = kMegaRows * (kMegaConsumerWarps / p.ks);
+            if ((rows_per_cta + kMegaRows - 1 + rows_per_round - 1) / rows_per_round > 4) return no("tensor-parallel megakernel: more than 4 row rounds per CTA in a row-parallel phase");
+        }
+    }
     if (c->nkv_l > G) return no("more kv heads than SMs");
     c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
     const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
@@ -743,8 +767,10 @@ void mega_setup(b2l_ctx* c) {
     c->mega_stages = stages;
     c->mega_smem = static_cast<size_t>(stages) * kMegaStageBytes + fixed;
     if (const char* e = std::getenv("B2L_MEGA_LL")) c->mega_ll = std::atoi(e) != 0;
-    for (int v = 0; v < 2; v++) {
-        auto kern = v ? mega_decode_kernel<true> : mega_decode_kernel<false>;
+    if (c->p.tp_size > 1) c->mega_ll = true;   // the tensor-parallel kernel exists in the dataflow build only
+    for (int v = 0; v < 3; v++) {
+        if ((v == 2) != (c->p.tp_size > 1)) continue;   // v 0/1: single-GPU kernel (barrier / dataflow build), v 2: tensor-parallel rank
+        void (*kern)() = v == 2 ? megatp::mega_decode_kernel<true> : v == 1 ? mega1::mega_decode_kernel<true> : mega1::mega_decode_kernel<false>;
         B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->mega_smem)));
         // the kernel calls non-inlined device functions: make sure the per-thread stack covers its frames
         cudaFuncAttributes fa{};
@@ -772,12 +798,12 @@ void mega_setup(b2l_ctx* c) {
         c->mega_ll_keys = zalloc(static_cast<size_t>(2) * G);
         c->mega_seq = 0;
     }
+    c->mega_bar = dalloc<unsigned long long>(c, 8);
+    B2L_CUDA(cudaMemset(c->mega_bar, 0, sizeof(unsigned long long) * 8));
     MegaPhase* d = dalloc<MegaPhase>(c, ph.size());
     B2L_CUDA(cudaMemcpy(d, ph.data(), sizeof(MegaPhase) * ph.size(), cudaMemcpyHostToDevice));
     c->mega_phases = d;
     c->mega_n_phases = static_cast<int>(ph.size());
-    c->mega_bar = dalloc<unsigned long long>(c, 8);
-    B2L_CUDA(cudaMemset(c->mega_bar, 0, sizeof(unsigned long long) * 8));
     B2L_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->mega_abort), sizeof(int) * 1024, cudaHostAllocMapped));
     std::memset(c->mega_abort, 0, sizeof(int) * 1024);
     {   // L2 persistence for the KV cache (B2L_MEGA_L2PERSIST=0 disables)
@@ -818,6 +844,16 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
     a.ll_h = c->mega_ll_h; a.ll_qkv = c->mega_ll_qkv; a.ll_act = c->mega_ll_act; a.ll_pacc = c->mega_ll_pacc;
     a.ll_pml = c->mega_ll_pml; a.ll_keys = c->mega_ll_keys;
     a.seq_base = c->mega_seq;
+    a.tp = c->p.tp_size; a.tp_rank = c->p.tp_rank; a.vocab_base = c->p.tp_rank * c->V_l; a.Hpad = c->H;
+    if (a.tp > 1) {
+        for (int p = 0; p < a.tp; p++) {
+            a.tp_slab[p] = reinterpret_cast<unsigned long long*>(c->tp_peer[p] + c->tp_mega_off);
+            a.tp_keys[p] = reinterpret_cast<unsigned long long*>(c->tp_peer[p] + c->tp_keys_off);
+        }
+        a.ll_keys = a.tp_keys[a.tp_rank];   // this rank's array: every rank's CTAs store their keys here
+    } else {
+        a.tp_keys[0] = c->mega_ll_keys;
+    }
     a.poll_sleep_ns = std::getenv("B2L_MEGA_POLL_NS") ? std::atoi(std::getenv("B2L_MEGA_POLL_NS")) : 0;
     a.ll_use_sentinel = std::getenv("B2L_MEGA_SENTINEL") ? std::atoi(std::getenv("B2L_MEGA_SENTINEL")) : 0;
     if (c->mega_ll) c->mega_seq += static_cast<uint32_t>(n_steps) * static_cast<uint32_t>(c->mega_n_phases);
@@ -839,7 +875,6 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
     a.attn_tps = c->mega_attn_tps;
     a.producer_sleep_ns = std::getenv("B2L_MEGA_PSLEEP") ? std::atoi(std::getenv("B2L_MEGA_PSLEEP")) : 100;
     a.l2_ahead = c->mega_l2_ahead;
-    if (!c->mega_ll) B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));   // argmax keys of the barrier build
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->prop.multiProcessorCount);
     cfg.blockDim = dim3(kMegaThreads);
@@ -860,9 +895,15 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
         attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.numAttrs = 2;
     }
-    B2L_CUDA(cudaMemcpyToSymbolAsync(c_mega, &a, sizeof(MegaArgs), 0, cudaMemcpyHostToDevice, c->stream));
-    if (c->mega_ll) B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel<true>));
-    else B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_decode_kernel<false>));
+    if (!c->mega_ll) B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));   // argmax keys of the barrier build
+    if (a.tp > 1) {
+        B2L_CUDA(cudaMemcpyToSymbolAsync(megatp::c_mega, &a, sizeof(MegaArgs), 0, cudaMemcpyHostToDevice, c->stream));
+        B2L_CUDA(cudaLaunchKernelEx(&cfg, megatp::mega_decode_kernel<true>));
+    } else {
+        B2L_CUDA(cudaMemcpyToSymbolAsync(mega1::c_mega, &a, sizeof(MegaArgs), 0, cudaMemcpyHostToDevice, c->stream));
+        if (c->mega_ll) B2L_CUDA(cudaLaunchKernelEx(&cfg, mega1::mega_decode_kernel<true>));
+        else B2L_CUDA(cudaLaunchKernelEx(&cfg, mega1::mega_decode_kernel<false>));
+    }
     c->launched++;
 }
 
@@ -1204,6 +1245,11 @@ int b2l_shard_window(const b2l_params* p, const char* hf_name, const int64_t* sh
         g_create_error = e.what();
         return 1;
     }
+}
+
+int b2l_is_model_tensor(const char* hf_name) {
+    int layer;
+    return hf_name && parse_name(hf_name, &layer) != K_BAD ? 1 : 0;
 }
 
 int b2l_finalize(b2l_ctx* c) {

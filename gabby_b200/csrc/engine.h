@@ -100,9 +100,9 @@ struct b2l_ctx {
     uint16_t* kv_base = nullptr;     // all layers' KV pools, contiguous
     size_t mega_l2_persist_bytes = 0;
     int mega_inflight = 0, mega_l2_ahead = 0, mega_attn_tps = 128;
-    unsigned long long *mega_bar = nullptr;  // [0] counter, [1] epoch, [2..4] argmax keys
+    unsigned long long *mega_bar = nullptr;  // [0] counter, [1] epoch, [2..4] argmax keys (barrier build)
+    bool mega_ll = true;                     // dataflow build (B2L_MEGA_LL=0: the grid-barrier build, single GPU only)
     // dataflow mode: {value, seq} word buffers (h | qkv | act | attention partials | per-CTA argmax keys)
-    bool mega_ll = true;
     unsigned long long *mega_ll_h = nullptr, *mega_ll_qkv = nullptr, *mega_ll_act = nullptr, *mega_ll_pacc = nullptr,
                        *mega_ll_pml = nullptr, *mega_ll_keys = nullptr;
     uint32_t mega_seq = 0;                   // sequence numbers consumed by earlier launches
@@ -137,7 +137,8 @@ struct b2l_ctx {
     float* tp_vals = nullptr;        // [max_rows] local max values
     // row-parallel partial sums over NVLink peer memory (cudaIpc-mapped slabs, LL words): see TpSend
     bool tp_peer_ok = false;         // false: NCCL all-reduce transport
-    uint2* tp_ll = nullptr;          // this rank's slabs [2 slots][tp][max_rows][H]
+    uint2* tp_ll = nullptr;          // this rank's slabs [2 slots][tp][max_rows][H], then the megakernel's [2][tp][H] and its keys [tp][2 SMs]
+    size_t tp_mega_off = 0, tp_keys_off = 0;   // word offsets of the megakernel regions inside tp_ll
     uint2* tp_peer[8] = {};          // every rank's slab base as mapped here (own = tp_ll)
     uint32_t* tp_seq = nullptr;      // [2] sequence number per slot
     unsigned int* tp_done = nullptr; // [2] last-CTA counters of the receiver kernel

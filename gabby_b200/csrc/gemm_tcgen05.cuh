@@ -14,7 +14,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
-#include "mega_decode.cuh"  // mbarrier / smem helpers
+#include "ptx_helpers.cuh"  // mbarrier / smem helpers
 
 namespace b2l {
 

@@ -37,193 +37,27 @@
 //
 // HBM sees one sequential read of the model per token; everything else lives in L2 / smem.
 // Math is identical to decode_kernels.cuh (the multi-kernel path) up to fp32 summation order.
-#pragma once
+// This file is compiled TWICE by engine.cu (no include guard): MEGA_TP 0 in namespace b2l::mega1 is the single-GPU kernel,
+// MEGA_TP 1 in namespace b2l::megatp the kernel of a tensor-parallel rank. The tensor-parallel additions are confined to
+// #if MEGA_TP blocks so that the single-GPU kernel stays instruction for instruction what was tuned in round 1 (the same
+// additions behind run-time flags cost it 6-10 %: the kernel's schedule is sensitive to every extra call and branch).
 #include "common.cuh"
 #include "decode_kernels.cuh"
+#include "mega_common.cuh"
+#include "ptx_helpers.cuh"
+#if !defined(MEGA_TP) || !defined(MEGA_NS)
+#error "define MEGA_TP (0 or 1) and MEGA_NS before including mega_decode.cuh"
+#endif
 
 namespace b2l {
+namespace MEGA_NS {
+static_assert(kPtxConsumerThreads == kMegaConsumerThreads, "consumer_bar() counts the megakernel's consumer threads");
 
-constexpr int kMegaConsumerWarps = 8;
-constexpr int kMegaConsumerThreads = kMegaConsumerWarps * 32;
-constexpr int kMegaThreads = kMegaConsumerThreads + 32;  // + producer warp
-constexpr int kMegaStageBytes = 16 * 1024;
-constexpr int kMegaMaxStages = 12;
-constexpr int kMegaRows = 4;  // rows one warp reduces together (transposed butterfly)
-constexpr int kMegaXsFloats = 2048;
-constexpr int kMegaProfRows = 16 + 2 * 160;  // debug timeline: 16 summary rows, then per CTA: input-ready and phase-end times
-
-enum MegaPhaseType { PH_QKV = 0, PH_ATTN = 1, PH_OPROJ = 2, PH_GATEUP = 3, PH_DOWN = 4, PH_LMHEAD = 5 };
-
-struct MegaPhase {
-    int type, layer;
-    const uint16_t* W;       // [N][K] bf16 (PH_ATTN: unused)
-    const uint16_t* norm_w;  // fused RMSNorm weight or null
-    uint16_t* kv_pool;       // PH_ATTN: this layer's KV pool
-    int N, K;
-    int ks;                  // warps per row (K split into ks slices of 256*m elements)
-    int m;                   // 16-byte sweeps per warp unit: slice = 256 * m elements (<= 2048)
-};
-
-struct MegaArgs {
-    const MegaPhase* phases;
-    int n_phases;
-    int n_stages;
-    // model
-    const uint16_t* embed;
-    const float* rope;
-    int H, V, nh, nkv, hd, I;
-    float eps, attn_scale;
-    // activations (fp32, L2 resident)
-    float *h, *qkv, *attn, *act, *logits;
-    // paged KV
-    const int32_t* block_table;
-    int page_size, kvd;
-    float *part_acc, *part_ml;
-    int* attn_counters;
-    int nsplit_max;
-    // token loop
-    int32_t token0, pos0;  // arg_io != 0: first token / position travel in this struct (constant memory) instead of *token / *position
-    int arg_io;
-    int32_t* token;      // in: first token; out: last argmax
-    int32_t* position;   // in: first position; out: advanced
-    int32_t* out_ids;    // [n_steps]
-    int n_steps;
-    // sync
-    unsigned long long* bar_counter;  // monotonically increasing arrivals
-    unsigned long long* bar_epoch;    // arrivals consumed by previous launches
-    unsigned long long* argmax_keys;  // [3]
-    int* abort_flag;     // mapped pinned host memory: [0] abort code, [1 + cta] progress marker of each CTA (debug)
-    int debug_nostream;  // 1: copy 16 bytes per chunk instead of the weights (timing experiments only; wrong results)
-    int debug_progress;  // 1: CTAs record step*100000 + phase*100 + stage-of-phase
-    int producer_sleep_ns;
-    int attn_tps;       // context tokens per attention split (work item)
-    int max_inflight;   // bulk copies issued but not yet landed, per CTA (bounds queueing latency in L2/HBM)
-    int l2_ahead;       // chunks prefetched into L2 beyond the ring (0 = off)
-    // dataflow mode (kernel template LL): activations travel as 8-byte {fp32 bits, sequence number} words and every
-    // reader polls for the sequence number of the phase that produces its input -- no grid barrier anywhere
-    unsigned long long *ll_h, *ll_qkv, *ll_act, *ll_pacc, *ll_pml, *ll_keys;
-    uint32_t seq_base;  // sequence numbers used by earlier launches
-    int poll_sleep_ns;    // back-off between failed polls of the dataflow words
-    int ll_use_sentinel;  // 1: one lane per warp polls first, then everybody loads; 0: everybody polls its own words
-    unsigned long long* prof;  // optional [9][n_phases + 1], see b2l_debug_mega_profile globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
-};
 
 // The launch arguments live in __constant__ memory: the device functions below read them as
 // constant-bank operands (no reloads after inline-asm memory clobbers, no generic loads through a
 // pointer to the parameter space). One megakernel launch per device at a time (host side locks).
 __constant__ MegaArgs c_mega;
-
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// ---- PTX helpers ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// non-blocking probe (try_wait may suspend the thread for a hardware-defined time before failing)
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// a deadlock here would hang the GPU: bound every wait and trap with a reason code instead.
-// Everything is inline (no calls in the hot loops: a call forces ABI spills around it).
-__device__ __forceinline__ void mega_die(int* abort_flag, int code) {
-    *reinterpret_cast<volatile int*>(abort_flag) = code;  // mapped pinned host memory
-    __threadfence_system();
-    __nanosleep(2000000);  // give the store time to reach the host before the context dies
-    __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    unsigned spins = 0;  // try_wait suspends for a hardware-defined interval per attempt
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) mega_die(abort_flag, code);
-    }
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
-        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-// ptxas is free to reorder plain shared loads; it serialised the weight loads row by row (one destination register,
-// every FFMA2 chain waiting on its own load). Volatile loads keep the program order: a full step of prefetch.
-__device__ __forceinline__ uint4 lds128_ordered(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ float4 lds128f(uint32_t addr) {
-    float4 r;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ void sts128f(uint32_t addr, const float4& v) {
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float lds32f(uint32_t addr) {
-    float r;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ void sts32f(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-__device__ __forceinline__ unsigned long long lds64(uint32_t addr) {
-    unsigned long long r;
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(r) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ void sts64(uint32_t addr, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory"); }
-__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kMegaConsumerThreads) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // rows [r0, r1) of an N-row matrix owned by CTA `c` of `G` (unit = 2 rows for SwiGLU pairs)
 // Loads that must be ISSUED where they are written (ahead of a wait they are meant to overlap): __ldcg / __ldg are
@@ -253,6 +87,22 @@ __device__ __forceinline__ uint4 ll_ld2(const unsigned long long* p) {  // .x/.z
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p) : "memory");
     return w;
 }
+#if MEGA_TP
+// words written by another GPU over NVLink: system scope
+__device__ __forceinline__ void ll_st_sys(unsigned long long* p, float v, uint32_t seq) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"((static_cast<unsigned long long>(seq) << 32) | __float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ uint4 ll_ld2_sys(const unsigned long long* p) {
+    uint4 w;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(p) : "memory");
+    return w;
+}
+__device__ __forceinline__ uint2 ll_ld1_sys(const unsigned long long* p) {   // .x value, .y sequence number
+    uint2 w;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p) : "memory");
+    return w;
+}
+#endif
 // one lane per warp watches the first word pair of the warp's region until it carries `seq`: the whole grid polling
 // every word would cost terabytes per second of L2 traffic while the slowest producer finishes
 __device__ __forceinline__ void ll_sentinel(const unsigned long long* p, uint32_t seq, int lane, int* abort_flag, int code) {
@@ -555,17 +405,26 @@ __device__ __forceinline__ int mega_poll_token(const MegaSmem& sm, uint32_t want
     const MegaArgs& a = c_mega;
     const int lane = tid & 31, w = tid >> 5;
     unsigned long long best = 0ull;
-    for (int c = tid; c < static_cast<int>(gridDim.x); c += kMegaConsumerThreads) {
+#if MEGA_TP
+    const int n_keys = a.tp * static_cast<int>(gridDim.x);   // every CTA of every rank stores its key into this rank's array
+#else
+    const int n_keys = static_cast<int>(gridDim.x);
+#endif
+    for (int c = tid; c < n_keys; c += kMegaConsumerThreads) {
         unsigned spins = 0;
         for (;;) {
+#if MEGA_TP
+            const uint4 wk = ll_ld2_sys(a.ll_keys + 2 * c);
+#else
             const uint4 wk = ll_ld2(a.ll_keys + 2 * c);
+#endif
             if (wk.y == want && wk.w == want) {
                 const unsigned long long k = (static_cast<unsigned long long>(wk.x) << 32) | wk.z;
                 best = k > best ? k : best;
                 break;
             }
             __nanosleep(32);
-            if (++spins > (1u << 22)) mega_die(a.abort_flag, 130);
+            if (++spins > (MEGA_TP ? (1u << 25) : (1u << 22))) mega_die(a.abort_flag, 130);   // ranks may start a launch milliseconds apart
         }
     }
 #pragma unroll
@@ -583,6 +442,54 @@ __device__ __forceinline__ int mega_poll_token(const MegaSmem& sm, uint32_t want
     }
     return argmax_key_index(best);
 }
+
+#if MEGA_TP
+// Tensor parallel, row-parallel phases (O-proj, down): second pass over the rows this lane produced. The tp partial sums of
+// a row arrive over NVLink in this rank's own slab; they are added to the residual in rank order -- every rank computes
+// bit-identical h -- and the row is published locally like any other activation word. One round of rows at a time, the
+// tp loads of a row in flight together (out of line: its registers must not weigh on the streaming loop).
+__device__ __noinline__ void mega_tp_collect(const PhaseRegs ph, uint32_t gp, int token, int tid) {
+    const MegaArgs& a = c_mega;
+    constexpr int kMaxTp = 8;
+    const int lane = tid & 31, w = tid >> 5;
+    const int ks_shift = ph.ks == 1 ? 0 : ph.ks == 2 ? 1 : 2;
+    const int q = w & (ph.ks - 1), rloc = w >> ks_shift, my_t = lane >> 3;
+    if ((lane & 7) != 0 || q != 0) return;   // the lanes that held the row sums of the phase
+    const int r0 = ph.r0, r1 = ph.r1;
+    const int groups_per_round = kMegaConsumerWarps >> ks_shift;
+    const int n_groups = (r1 - r0 + kMegaRows - 1) / kMegaRows;
+    const int n_rounds = (n_groups + groups_per_round - 1) >> (3 - ks_shift);
+    const bool resid_h = ph.type == PH_DOWN || (ph.type == PH_OPROJ && ph.layer != 0);
+    const bool resid_e = ph.type == PH_OPROJ && ph.layer == 0;
+    const unsigned long long* slab = a.tp_slab[a.tp_rank] + (static_cast<size_t>(ph.type == PH_DOWN ? 1 : 0) * a.tp) * a.Hpad;
+    for (int rd = 0; rd < n_rounds; rd++) {
+        const int rg = rd * groups_per_round + rloc, row_t = r0 + rg * kMegaRows + my_t;
+        if (rg >= n_groups || row_t >= r1) continue;
+        float sum = 0.f;
+        if (resid_h) sum = ld_cg_early_f32(a.ll_h + ll_perm(row_t));
+        else if (resid_e) sum = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row_t]);
+        const unsigned long long* src = slab + ll_perm(row_t);
+        unsigned spins = 0;
+        for (;;) {
+            uint2 wv[kMaxTp];
+#pragma unroll
+            for (int p = 0; p < kMaxTp; p++)
+                if (p < a.tp) wv[p] = ll_ld1_sys(src + static_cast<size_t>(p) * a.Hpad);
+            bool ok = true;
+#pragma unroll
+            for (int p = 0; p < kMaxTp; p++) ok = ok && (p >= a.tp || wv[p].y == gp);
+            if (ok) {
+#pragma unroll
+                for (int p = 0; p < kMaxTp; p++)
+                    if (p < a.tp) sum += __uint_as_float(wv[p].x);
+                break;
+            }
+            if (++spins > (1u << 25)) mega_die(a.abort_flag, 230 + ph.type);
+        }
+        ll_st(a.ll_h + ll_perm(row_t), sum, gp);
+    }
+}
+#endif
 
 // ---- one GEMV-type phase for one CTA ---------------------------------------------------------
 #ifdef MEGA_GEMV_INLINE
@@ -782,6 +689,11 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
     const int n_stage_total = (r1 - r0 + RS - 1) >> rs_shift;           // stages the producer fills for this phase
     const bool resid_h = type == PH_DOWN || (type == PH_OPROJ && ph.layer != 0);
     const bool resid_e = type == PH_OPROJ && ph.layer == 0;
+#if MEGA_TP
+    const bool tp_phase = type == PH_OPROJ || type == PH_DOWN;   // K-sharded: this rank holds a partial sum of every row
+#else
+    constexpr bool tp_phase = false;
+#endif
     const int my_t = lane >> 3;                         // after the butterfly, lane 8*t holds row t of the item
     const bool out_lane = (lane & 7) == 0;
     const bool hi16 = lane & 16, hi8 = lane & 8;
@@ -809,7 +721,7 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
         const int row_t = row0 + my_t;
         const bool row_live = live && row_t < r1;
         float resid = 0.f;  // residual input, fetched before the wait so its L2 latency overlaps
-        if (out_lane && row_live && q == 0) {
+        if (out_lane && row_live && q == 0 && !tp_phase) {   // (a tensor-parallel rank adds the residual when it collects the partial sums)
             if (resid_h) resid = LL ? ld_cg_early_f32(a.ll_h + ll_perm(row_t)) : ld_cg_early_f32(a.h + row_t);
             else if (resid_e) resid = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + row_t]);
         }
@@ -936,11 +848,18 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
                 }
             } else if (type == PH_LMHEAD) {
                 a.logits[row_t] = s;
-                const unsigned long long key = argmax_key(s, row_t);
+                const unsigned long long key = argmax_key(s, (MEGA_TP ? a.vocab_base : 0) + row_t);   // global vocabulary index
                 best_key = key > best_key ? key : best_key;
             } else {
+#if MEGA_TP
+                {   // partial sum -> every rank's slab (own included) over NVLink, one 8-byte word each
+                    const size_t off = (static_cast<size_t>(type == PH_DOWN ? 1 : 0) * a.tp + a.tp_rank) * a.Hpad + ll_perm(row_t);
+                    for (int p = 0; p < a.tp; p++) ll_st_sys(a.tp_slab[p] + off, s, gp);
+                }
+#else
                 if (LL) ll_st(a.ll_h + ll_perm(row_t), resid + s, gp);  // O-proj / down: residual add
                 else a.h[row_t] = resid + s;
+#endif
             }
         }
 #ifdef MEGA_PROF_ROUNDS
@@ -1434,6 +1353,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                 }
 #endif
             }
+#if MEGA_TP
+            if (ph.type == PH_OPROJ || ph.type == PH_DOWN)   // collect the tp partial sums of this CTA's rows, publish h locally
+                mega_tp_collect(ph, a.seq_base + static_cast<uint32_t>(step * a.n_phases + pi) + 1u, st.token, tid);
+#endif
             if (ph.type == PH_LMHEAD) {
                 // CTA-level argmax, then one atomicMax per CTA on this step's key
                 const int lane = tid & 31, w = tid >> 5;
@@ -1453,9 +1376,16 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                     }
                     if (LL) {
                         const uint32_t gp = a.seq_base + static_cast<uint32_t>(step * a.n_phases + pi) + 1u;
+#if MEGA_TP
+                        for (int p = 0; p < a.tp; p++)   // every rank takes the maximum over all ranks' CTAs itself
+                            asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(a.tp_keys[p] + 2 * (a.tp_rank * gridDim.x + blockIdx.x)),
+                                         "l"((static_cast<unsigned long long>(gp) << 32) | (k >> 32)),
+                                         "l"((static_cast<unsigned long long>(gp) << 32) | (k & 0xffffffffull)) : "memory");
+#else
                         asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(a.ll_keys + 2 * blockIdx.x),
                                      "l"((static_cast<unsigned long long>(gp) << 32) | (k >> 32)),
                                      "l"((static_cast<unsigned long long>(gp) << 32) | (k & 0xffffffffull)) : "memory");
+#endif
                     } else {
                         atomicMax(a.argmax_keys + (step % 3), k);
                     }
@@ -1488,4 +1418,5 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     }
 }
 
+}  // namespace MEGA_NS
 }  // namespace b2l

@@ -3,16 +3,19 @@
 // the static Load(std::unique_ptr<InferenceConfig>) factory); Generate() runs the B200 forward through
 // the b2l C-ABI instead of returning a constant string (generator.cc:33-38).
 #pragma once
+#include <condition_variable>
 #include <cstdint>
 #include <memory>
 #include <mutex>
 #include <ostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "config.h"
 #include "kv_allocator.h"
 #include "sampler.h"
+#include "scheduler.h"
 #include "tokenizer.h"
 
 struct b2l_ctx;
@@ -42,14 +45,16 @@ struct GeneratorOptions {
     int device = 0;
     int max_positions = 2048;   // per-sequence context capacity (RoPE table rows, block-table length)
     int page_size = 16;
-    int num_pages = 0;          // 0: enough for one sequence of max_positions
-    int max_new_tokens = 256;
+    int num_pages = 0;          // 0: enough for max_batch sequences of max_positions
+    int max_new_tokens = 256;   // default completion budget of Generate (a request's max_tokens overrides it)
+    int max_batch = 8;          // sequences decoded together: concurrent Generate calls share decode steps (continuous batching)
 };
 
 struct GenerationResult {
     std::vector<int32_t> tokens;   // generated ids (EOS excluded)
-    FinishReason finish = FinishReason::kNone;
-    int prompt_tokens = 0;
+    FinishReason finish = FinishReason::kNone;   // kStop: EOS ("stop"), kLength: the token budget ran out ("length")
+    int prompt_tokens = 0;         // usage.prompt_tokens; usage.completion_tokens = tokens.size()
+    std::string text;              // detokenized completion (GenerateDetailed only)
 };
 
 class Llama3Generator : public Generator {
@@ -61,8 +66,15 @@ public:
     static std::unique_ptr<Generator> Load(std::unique_ptr<InferenceConfig> config);
     static std::unique_ptr<Llama3Generator> Load(std::unique_ptr<InferenceConfig> config, const GeneratorOptions& opt);
 
-    // token-level entry (bench / parity tests): prefill + greedy decode until EOS or max_new_tokens
+    // What gabby's service.cc:79-116 hard-codes ("usage" counts, finish_reason "stop") comes from here: the completion text
+    // together with prompt / completion token counts and the real finish reason; max_tokens <= 0 = the configured default.
+    GenerationResult GenerateDetailed(const Request& req, int max_tokens);
+
+    // token-level entry (bench / parity tests): prefill + greedy decode until EOS or max_new_tokens.
+    // device_loop = false: the request joins the continuous-batching queue (concurrent callers share decode steps);
+    // device_loop = true: one exclusive device-resident loop (token feedback never leaves the GPU).
     GenerationResult GenerateTokens(const std::vector<int32_t>& prompt, int max_new_tokens, bool device_loop);
+    SchedulerStats scheduler_stats();
 
     const LlamaParams& params() const { return params_; }
     Tokenizer& tokenizer() { return *tokenizer_; }
@@ -78,7 +90,17 @@ private:
     b2l_ctx* ctx_ = nullptr;
     std::unique_ptr<KvPageAllocator> kv_;
     std::unique_ptr<Tokenizer> tokenizer_;
-    std::mutex mu_;   // Generate is called from HTTP worker threads (reference: http/server.h:35)
+    // Generate is called from HTTP worker threads (reference: http/server.h:35). Requests queue in the scheduler; ONE stepping
+    // thread drives the engine (admission + one decode step of every running sequence per iteration), callers wait for
+    // their own result. mu_ guards scheduler, allocator and engine.
+    void StepLoop();
+    int capacity_ = 0;   // tokens one sequence can hold: min(block-table reach, max_positions)
+    std::unique_ptr<B2lBatchEngine> batch_engine_;
+    std::unique_ptr<BatchScheduler> sched_;
+    std::mutex mu_;
+    std::condition_variable work_cv_, done_cv_;
+    std::thread stepper_;
+    bool stop_ = false;
 };
 
 }  // namespace inference

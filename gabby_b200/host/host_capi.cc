@@ -1,4 +1,5 @@
 // host_capi.cc -- C view of the host layer (include/gabby_b200_host.h).
+#include <algorithm>
 #include <cstring>
 #include <exception>
 #include <stdexcept>
@@ -98,14 +99,36 @@ int gb_generator_generate(gb_generator* g, const char* system_text, const char* 
     });
 }
 
-int gb_generator_generate_ids(gb_generator* g, const int32_t* prompt, int n_prompt, int max_new_tokens, int device_loop,
-                              int32_t* out_ids, int* n_out, int* finish) {
+int gb_generator_generate_detailed(gb_generator* g, const char* system_text, const char* user_text, int max_tokens, char* out, int cap,
+                                   int* prompt_tokens, int* completion_tokens, int* finish) {
     return guarded([&] {
-        if (!g || !prompt || !out_ids || !n_out) throw std::runtime_error("gb_generator_generate_ids: null argument");
-        const GenerationResult r = g->gen->GenerateTokens(std::vector<int32_t>(prompt, prompt + n_prompt), max_new_tokens, device_loop != 0);
-        *n_out = static_cast<int>(r.tokens.size());
-        std::memcpy(out_ids, r.tokens.data(), r.tokens.size() * sizeof(int32_t));
+        if (!g || !out || cap <= 0) throw std::runtime_error("gb_generator_generate_detailed: bad argument");
+        const GenerationResult r = g->gen->GenerateDetailed(Request{Message{"system", system_text ? system_text : ""},
+                                                                     Message{"user", user_text ? user_text : ""}}, max_tokens);
+        std::snprintf(out, static_cast<size_t>(cap), "%s", r.text.c_str());
+        if (prompt_tokens) *prompt_tokens = r.prompt_tokens;
+        if (completion_tokens) *completion_tokens = static_cast<int>(r.tokens.size());
         if (finish) *finish = r.finish == FinishReason::kStop ? 1 : r.finish == FinishReason::kLength ? 2 : 0;
+    });
+}
+
+int gb_generator_generate_ids(gb_generator* g, const int32_t* prompt, int n_prompt, int max_new_tokens, int device_loop,
+                              int32_t* out_ids, int out_cap, int* n_out, int* finish) {
+    return guarded([&] {
+        if (!g || !prompt || !out_ids || !n_out || out_cap < 0) throw std::runtime_error("gb_generator_generate_ids: bad argument");
+        const GenerationResult r = g->gen->GenerateTokens(std::vector<int32_t>(prompt, prompt + n_prompt), max_new_tokens, device_loop != 0);
+        *n_out = static_cast<int>(r.tokens.size());   // the true count; at most out_cap ids are copied
+        std::memcpy(out_ids, r.tokens.data(), std::min(r.tokens.size(), static_cast<size_t>(out_cap)) * sizeof(int32_t));
+        if (finish) *finish = r.finish == FinishReason::kStop ? 1 : r.finish == FinishReason::kLength ? 2 : 0;
+    });
+}
+
+int gb_generator_sched_stats(gb_generator* g, int64_t* out) {
+    return guarded([&] {
+        if (!g || !out) throw std::runtime_error("gb_generator_sched_stats: null argument");
+        const SchedulerStats st = g->gen->scheduler_stats();
+        const int64_t v[8] = {st.steps, st.prefill_calls, st.decode_calls, st.prefill_tokens, st.decode_tokens, st.preemptions, st.max_concurrent, -1};
+        std::memcpy(out, v, sizeof(v));
     });
 }
 

@@ -57,6 +57,19 @@ const SchedResult& BatchScheduler::Result(int id) const {
     return it->second;
 }
 
+void BatchScheduler::Forget(int id) {
+    auto it = results_.find(id);
+    if (it != results_.end() && it->second.done) results_.erase(it);
+}
+
+void BatchScheduler::Fail(Seq& s, const std::string& why) {
+    SchedResult& r = results_[s.id];
+    r.error = why;
+    r.done = true;
+    if (s.kv_seq >= 0) kv_->Free(s.kv_seq);
+    s.kv_seq = -1;
+}
+
 void BatchScheduler::Retire(Seq& s, FinishReason why) {
     SchedResult& r = results_[s.id];
     r.finish = why;
@@ -88,7 +101,10 @@ int BatchScheduler::Admit() {
         if (n > budget) break;                       // FIFO: do not let short requests overtake a long one forever
         const int kv_seq = kv_->NewSequence();
         try {
-            kv_->Reserve(kv_seq, n + 1);              // the prompt and the position of the first generated token
+            // the prompt, the first generated token and -- unless that one already ends the request -- the token this
+            // step's decode produces
+            const int remaining = w.max_new - static_cast<int>(results_[w.id].tokens.size());
+            kv_->Reserve(kv_seq, n + std::min(2, std::max(1, remaining)));
         } catch (const KvOutOfPages&) {
             kv_->Free(kv_seq);
             break;                                    // wait for running sequences to finish (or be preempted)
@@ -109,7 +125,13 @@ int BatchScheduler::Admit() {
         kv_ids[i] = batch[i].kv_seq;
     }
     const std::vector<int32_t> bt = kv_->BatchTable(kv_ids);
-    engine_->Prefill(n_seq, tokens.data(), q_lens.data(), start.data(), bt.data(), mb, next.data());
+    try {
+        engine_->Prefill(n_seq, tokens.data(), q_lens.data(), start.data(), bt.data(), mb, next.data());
+    } catch (const std::exception& e) {
+        // the requests are already off the queue and hold pages: fail them explicitly instead of leaking both
+        for (Seq& s : batch) Fail(s, e.what());
+        throw;
+    }
     stats_.prefill_calls++;
     stats_.prefill_tokens += static_cast<int64_t>(tokens.size());
     for (int i = 0; i < n_seq; i++) {
@@ -138,8 +160,9 @@ void BatchScheduler::PreemptYoungest() {
 
 int BatchScheduler::Step() {
     stats_.steps++;
-    int progressed = Admit();
-    // every running sequence needs room for the token it is about to produce
+    // 1. every RUNNING sequence needs room for the token it is about to produce; when the pool is short the youngest is
+    //    preempted -- before anything new is admitted, so that a fresh prompt is not prefilled just to be thrown away
+    bool preempted = false;
     for (;;) {
         bool ok = true;
         for (Seq& s : running_) {
@@ -153,7 +176,10 @@ int BatchScheduler::Step() {
         if (ok) break;
         if (running_.size() <= 1) throw std::runtime_error("BatchScheduler: KV pool too small for a single sequence");
         PreemptYoungest();
+        preempted = true;
     }
+    // 2. admit waiting requests into the free slots (not in a step that had to preempt: the pool is under pressure)
+    const int progressed = preempted ? 0 : Admit();
     stats_.max_concurrent = std::max(stats_.max_concurrent, static_cast<int>(running_.size()));
     if (running_.empty()) return progressed;
     const int n_seq = static_cast<int>(running_.size()), mb = kv_->max_blocks();
@@ -165,7 +191,13 @@ int BatchScheduler::Step() {
         kv_ids[i] = running_[i].kv_seq;
     }
     const std::vector<int32_t> bt = kv_->BatchTable(kv_ids);
-    engine_->Decode(n_seq, tokens.data(), positions.data(), bt.data(), mb, next.data());
+    try {
+        engine_->Decode(n_seq, tokens.data(), positions.data(), bt.data(), mb, next.data());
+    } catch (const std::exception& e) {
+        for (Seq& s : running_) Fail(s, e.what());
+        running_.clear();
+        throw;
+    }
     stats_.decode_calls++;
     stats_.decode_tokens += n_seq;
     std::vector<Seq> still;

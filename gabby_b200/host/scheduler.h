@@ -16,6 +16,7 @@
 #include <deque>
 #include <map>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "kv_allocator.h"
@@ -66,6 +67,7 @@ struct SchedResult {
     FinishReason finish = FinishReason::kNone;
     int prompt_tokens = 0;
     bool done = false;
+    std::string error;             // non-empty: the engine failed while this request was in flight (done is true)
 };
 
 class BatchScheduler {
@@ -81,6 +83,8 @@ public:
     void Drain();
 
     const SchedResult& Result(int id) const;
+    void Forget(int id);               // drop a finished request's result (long-running servers)
+    bool idle() const { return waiting_.empty() && running_.empty(); }
     int running() const { return static_cast<int>(running_.size()); }
     int waiting() const { return static_cast<int>(waiting_.size()); }
     const SchedulerStats& stats() const { return stats_; }
@@ -99,6 +103,7 @@ private:
     void Retire(Seq& s, FinishReason why);
     bool IsEos(int32_t id) const;
     int Admit();                       // prefill as many waiting requests as fit; returns how many
+    void Fail(Seq& s, const std::string& why);   // engine error: give the pages back, mark the request done with the message
     void PreemptYoungest();
 
     BatchEngine* engine_;

@@ -74,6 +74,10 @@ int b2l_synth_tensor(b2l_ctx* c, const char* hf_name, const int64_t* shape, int 
  * device needed -- b2l_upload_tensor / b2l_synth_tensor use exactly this window. q/k/v/gate/up and
  * lm_head are row (output) sharded, o/down column (input) sharded, norms and embeddings replicated. */
 int b2l_shard_window(const b2l_params* p, const char* hf_name, const int64_t* shape, int ndim, int64_t win[4]);
+/* 1 when `hf_name` is a tensor the forward uses (embeddings, norms, the seven projections of a layer, lm_head), 0 otherwise:
+ * checkpoints also carry buffers such as rotary_emb.inv_freq, which a loader skips instead of failing on them
+ * (the reference's Safetensors exposes every header entry alike: /root/reference/src/inference/safetensors.h:16-24). */
+int b2l_is_model_tensor(const char* hf_name);
 /* Checks every tensor arrived, builds derived layouts, captures decode graphs. */
 int b2l_finalize(b2l_ctx* c);
 void b2l_destroy(b2l_ctx* c);

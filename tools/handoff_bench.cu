@@ -17,7 +17,7 @@ constexpr int kStage = 16384, kStages = 8;
 
 struct P {
     unsigned long long* buf;   // [2][R][Kpad] words
-    int K, R, iters, variant, sleep_ns, stream, work_ns, jitter_ns;
+    int K, R, iters, variant, sleep_ns, stream, work_ns, jitter_ns, spin_sleep;
     const unsigned char* wbuf; // background stream source
     size_t wbytes;
     unsigned long long* counter;
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1) handoff(P p) {
             while (!stop) {
                 const int s = issued % kStages;
                 if (issued >= kStages) {
-                    while (!mbar_try(smem_u32(&bars[s]), parity[s])) { if (stop) break; }
+                    while (!mbar_try(smem_u32(&bars[s]), parity[s])) { if (stop) break; if (p.spin_sleep) __nanosleep(p.spin_sleep); }
                     parity[s] ^= 1;
                 }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(kStage) : "memory");
@@ -157,6 +157,29 @@ __global__ void __launch_bounds__(kThreads, 1) handoff(P p) {
                     if (++spins > (1ull << 25)) __trap();
                 }
             }
+        } else if (p.variant == 6) {
+            float acc = 0.f;
+            for (int k0 = w * 256; k0 < K; k0 += kWarps * 256) {
+                for (;;) {
+                    uint4 wd[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) wd[j] = ll_ld2(src + k0 + j * 64 + lane * 2);
+                    bool ok = true;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) ok = ok && wd[j].y == seq && wd[j].w == seq;
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc += __uint_as_float(wd[j].x) * __uint_as_float(wd[j].x) + __uint_as_float(wd[j].z) * __uint_as_float(wd[j].z);
+                        break;
+                    }
+                    if (p.sleep_ns) __nanosleep(p.sleep_ns);
+                    if (++spins > (1ull << 25)) __trap();
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            sink += rsqrtf(acc);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         } else if (p.variant == 1) {
             // each warp polls a 2048-word slice q = w & 3 into registers (no fan-out): 16 x 16-byte loads per lane in two halves
             const int q = w & (K / 2048 - 1);
@@ -239,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) handoff(P p) {
                 xs[k] = a.x; xs[k + 1] = a.z; xs[k + 2] = b.x; xs[k + 3] = b.z;
             }
         }
-        if (p.variant != 1 && p.variant != 5) {
+        if (p.variant != 1 && p.variant != 5 && p.variant != 6) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             // every warp reads the whole vector (<= 2048) / its slice and reduces it (RMSNorm sum of squares)
             float ss = 0.f;
@@ -304,17 +327,19 @@ int main(int argc, char** argv) {
                us, us - work_ns / 1000.0 - jitter_ns / 1000.0);
         fflush(stdout);
     };
-    for (int stream : {1, 0, 300, 1000}) {
-        for (int work : {0, 1500}) {
-            const int jit = work ? 500 : 0;
-            for (int K : {2048, 8192}) {
+    for (int spin : {0, 50}) {
+        p.spin_sleep = spin;
+        printf("--- stream warp sleeps %d ns between mbarrier probes\n", spin);
+        for (int stream : {1, 0, 100, 300}) {
+            for (int work : {0, 1500}) {
+                const int jit = work ? 500 : 0;
+                const int K = 2048;
                 run(0, K, 1, 0, stream, work, jit);
-                run(0, K, 4, 0, stream, work, jit);
-                run(0, K, 1, 100, stream, work, jit);
-                if (K > 2048) { run(1, K, 1, 0, stream, work, jit); run(1, K, 1, 100, stream, work, jit); }
-                else { run(5, K, 1, 0, stream, work, jit); run(5, K, 1, 100, stream, work, jit); }
-                run(2, K, 1, 0, stream, work, jit);
+                run(6, K, 1, 0, stream, work, jit);
+                run(0, K, 1, 300, stream, work, jit);
+                run(6, K, 1, 300, stream, work, jit);
                 run(3, K, 1, 0, stream, work, jit);
+                run(1, 8192, 1, 0, stream, work, jit);
             }
         }
     }
