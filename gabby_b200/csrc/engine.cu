@@ -758,6 +758,7 @@ void mega_setup(b2l_ctx* c) {
     }
     if (c->nkv_l > G) return no("more kv heads than SMs");
     c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
+    if (const char* e = std::getenv("B2L_MEGA_NSPLIT")) c->mega_nsplit = std::max(1, std::min(c->mega_nsplit, std::atoi(e)));   // tuning knob
     const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
     const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 64 + 128 + 4 * 2 * kMegaConsumerWarps * kMegaRows + sizeof(float) * kMegaXsFloats + 2 * static_cast<size_t>(c->H) + (48 + 8) * ph.size() + 16 + attn_scratch + 256;
     int max_smem = 0;

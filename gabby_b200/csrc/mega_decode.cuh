@@ -567,7 +567,13 @@ __device__ MEGA_GEMV_ATTR void mega_gemv_phase(const MegaArgs&, const PhaseRegs 
             // a warp fetches 256 consecutive words with four fully coalesced 16-byte loads per lane (512 contiguous
             // bytes per instruction), all in flight: one round trip for K <= 2048
             const unsigned long long* src = (type == PH_DOWN ? a.ll_act : a.ll_h);
+#ifdef MEGA_X_ROT
+            const int nblk = K >> 8;
+            for (int kb = w; kb < nblk; kb += kMegaConsumerWarps) {
+                const int k0 = ((kb + static_cast<int>(blockIdx.x)) % nblk) << 8;   // CTAs walk the vector in different orders: no L2 slice sees the whole grid at once
+#else
             for (int k0 = w * 256; k0 < K; k0 += kMegaConsumerWarps * 256) {
+#endif
                 unsigned spins = 0;
                 for (;;) {
                     uint4 wd[4];
@@ -901,6 +907,15 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
 
     // rotate-half RoPE of one 8-wide slice of a head living in the fused qkv row (element offset `head`)
     const uint32_t want = gp - 1u;
+#ifdef MEGA_X_ROPE_EARLY
+    float4 csr[4];   // (cos, sin) of this lane's 8 rotation pairs: fetched before any wait
+    {
+        const int d0e = sl * 8, j0e = d0e < HALF ? d0e : d0e - HALF;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(csr[i].x), "=f"(csr[i].y), "=f"(csr[i].z), "=f"(csr[i].w) : "l"(cs + 2 * (j0e + 2 * i)) : "memory");
+    }
+#endif
     auto rope_slice = [&](int head, float* out) {
         const int d0 = sl * 8, j0r = d0 < HALF ? d0 : d0 - HALF;  // the slice lies in one half (HALF % 8 == 0)
         float xx[16];
@@ -918,7 +933,11 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
         const float* x1 = xx + 8;
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
+#ifdef MEGA_X_ROPE_EARLY
+            const float4 c2 = csr[i >> 1];
+#else
             const float4 c2 = __ldg(reinterpret_cast<const float4*>(cs + 2 * (j0r + i)));  // (c, s, c', s')
+#endif
             out[i] = d0 < HALF ? x0[i] * c2.x - x1[i] * c2.y : x1[i] * c2.x + x0[i] * c2.y;
             out[i + 1] = d0 < HALF ? x0[i + 1] * c2.z - x1[i + 1] * c2.w : x1[i + 1] * c2.z + x0[i + 1] * c2.w;
         }
@@ -993,7 +1012,9 @@ __device__ __noinline__ void mega_attn_item(const MegaArgs&, uint16_t* kv_pool, 
                     const int page = __ldg(a.block_table + j / a.page_size), off = j % a.page_size;
                     *reinterpret_cast<uint4*>(kv.at(page, 0, off) + kvh * HD + sl * 8) = kw[u];
                     *reinterpret_cast<uint4*>(kv.at(page, 1, off) + kvh * HD + sl * 8) = vw[u];
+#ifndef MEGA_X_NOFENCE
                     if (LL) __threadfence();  // the cache line must be out before this item's partials announce the phase done
+#endif
                 }
             }
         }
@@ -1376,6 +1397,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                     }
                     if (LL) {
                         const uint32_t gp = a.seq_base + static_cast<uint32_t>(step * a.n_phases + pi) + 1u;
+#ifdef MEGA_X_NOFENCE
+                        // the K/V cache lines this CTA appended during the token (plain stores, ordered before this thread by the
+                        // CTA barriers since) must be visible before the key announces the token done: readers fence after the keys
+                        __threadfence();
+#endif
 #if MEGA_TP
                         for (int p = 0; p < a.tp; p++)   // every rank takes the maximum over all ranks' CTAs itself
                             asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(a.tp_keys[p] + 2 * (a.tp_rank * gridDim.x + blockIdx.x)),
