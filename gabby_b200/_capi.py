@@ -196,7 +196,7 @@ class Engine:
         (CTA 0 / last CTA), rows 16.. input-ready time per CTA, rows 176.. phase-end time per CTA"""
         n = C.c_int(0)
         self._ck(self.L.b2l_debug_mega_profile(self.h, int(enable), None, C.byref(n), None), "mega_profile")
-        ns = np.zeros((16 + 2 * 160, n.value + 1), dtype=np.uint64)   # kMegaProfRows
+        ns = np.zeros((16 + 2 * 160 + 64, n.value + 1), dtype=np.uint64)   # kMegaProfRows
         types = np.zeros(n.value, dtype=np.int32)
         self._ck(self.L.b2l_debug_mega_profile(self.h, int(enable), _p(ns), C.byref(n), _p(types)), "mega_profile")
         return ns, types

@@ -712,28 +712,57 @@ void upload_block_tables(b2l_ctx* c, int n_seq, const int32_t* bt, int max_block
 }
 
 // ---- persistent megakernel (mega_decode.cuh) ------------------------------------------------
-bool mega_shape(int K, int* ks, int* m) {
-    for (int s = 1; s <= 8; s *= 2) {
-        if (K % (s * 256) == 0 && K / (s * 256) <= 8) {
-            *ks = s;
-            *m = K / (s * 256);
-            return true;
-        }
-    }
-    return false;
+// Tiled weight image of one matrix for the megakernel: a permutation of the row-major [N][K] matrix (same size, no padding).
+// CTA c owns rows [r0, r1) (mega_row_range); they are taken in groups of <= 16 rows; a group of r rows occupies the same
+// r*K elements as in the row-major matrix, but ordered [K window of KS elements][16-byte piece of 8 k][row][8 elements]:
+// one window of a group is one contiguous bulk copy (r * KS * 2 bytes), and the 8 rows of an 8x8 `ldmatrix` tile are
+// 128 contiguous bytes (no bank conflicts for any r). One thread moves one 16-byte piece.
+__global__ void mega_tile_kernel(const uint4* __restrict__ W, uint4* __restrict__ Wt, int N, int K, int unit, int G) {
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int kc_per_row = K / 8;
+    if (idx >= static_cast<long long>(N) * kc_per_row) return;
+    const int row = static_cast<int>(idx / kc_per_row), kc = static_cast<int>(idx % kc_per_row);
+    const long long units = N / unit;
+    int c = static_cast<int>(static_cast<long long>(row / unit) * G / units);
+    int r0, r1;
+    mega_row_range(N, unit, c, G, r0, r1);
+    while (row >= r1) { c++; mega_row_range(N, unit, c, G, r0, r1); }
+    while (row < r0) { c--; mega_row_range(N, unit, c, G, r0, r1); }
+    const int g = (row - r0) / kMegaGroupRows, i = (row - r0) % kMegaGroupRows;
+    const int gr0 = r0 + g * kMegaGroupRows, r = min(kMegaGroupRows, r1 - gr0);
+    const int pieces = 1 << (mega_ks_shift(K) - 3);   // 16-byte pieces per window per row
+    const int p = kc / pieces, cc = kc % pieces;
+    Wt[static_cast<long long>(gr0) * kc_per_row + static_cast<long long>(p) * r * pieces + static_cast<long long>(cc) * r + i] = W[idx];
+}
+
+// the megakernel is instantiated for the (head_dim, GQA group) pairs of the supported models: Llama-3.2-1B (64, 4), 3B (128, 3),
+// Llama-3.1-8B (128, 4), 70B (128, 8), and the two test presets (32, 4) / (128, 2); a tensor-parallel rank keeps the group
+typedef void (*MegaKernel)();
+MegaKernel mega_kernel_for(int hd, int group, bool tp) {
+#define B2L_MEGA_CASE(H, G) if (hd == H && group == G) return tp ? static_cast<MegaKernel>(megatp::mega_decode_kernel<H, G>) : static_cast<MegaKernel>(mega1::mega_decode_kernel<H, G>);
+    B2L_MEGA_CASE(64, 4)
+    B2L_MEGA_CASE(128, 3)
+    B2L_MEGA_CASE(128, 4)
+    B2L_MEGA_CASE(128, 8)
+    B2L_MEGA_CASE(32, 4)
+    B2L_MEGA_CASE(128, 2)
+#undef B2L_MEGA_CASE
+    return nullptr;
 }
 
 void mega_setup(b2l_ctx* c) {
     c->mega_ok = false;
     auto no = [&](const std::string& why) { c->mega_why = why; };
     if (c->p.tp_size != 1 && !c->tp_peer_ok) return no("tensor-parallel megakernel needs the NVLink peer-memory transport");
+    if (!mega_kernel_for(c->hd, c->group, c->p.tp_size > 1)) return no("no megakernel instance for this (head_dim, GQA group)");
     const int G = c->prop.multiProcessorCount;
     std::vector<MegaPhase> ph;
+    int k_max = 0;
     auto add = [&](int type, int layer, const uint16_t* W, const uint16_t* norm, uint16_t* kv, int N, int K) -> bool {
         MegaPhase p{};
-        p.type = type; p.layer = layer; p.W = W; p.norm_w = norm; p.kv_pool = kv; p.N = N; p.K = K; p.ks = 1; p.m = 1;
-        if (type != PH_ATTN && !mega_shape(K, &p.ks, &p.m)) return false;
-        if (p.ks > kMegaRows) return false;  // a K slice of 4 rows must fit the 16 KB stages
+        p.type = type; p.layer = layer; p.W = W; p.norm_w = norm; p.kv_pool = kv; p.N = N; p.K = K; p.ks = 0; p.m = 0;
+        if (type != PH_ATTN && (K % 256 != 0 || N % 2 != 0)) return false;
+        k_max = std::max(k_max, K);
         ph.push_back(p);
         return true;
     };
@@ -747,31 +776,24 @@ void mega_setup(b2l_ctx* c) {
         ok = ok && add(PH_DOWN, l, w.w_down, nullptr, nullptr, c->H, c->I_l);
     }
     ok = ok && add(PH_LMHEAD, c->L, c->lm_head, c->final_norm, nullptr, c->V_l, c->H);
-    if (!ok) return no("a weight matrix has K that is not 256*m*ks with m<=8, ks in {1,2,4}");
-    if (c->p.tp_size > 1) {
-        // the row-parallel phases collect their tp partial sums in a second pass that is unrolled over <= 4 rounds of rows
-        for (const MegaPhase& p : ph) {
-            if (p.type != PH_OPROJ && p.type != PH_DOWN) continue;
-            const int rows_per_cta = (p.N + G - 1) / G, rows_per_round = kMegaRows * (kMegaConsumerWarps / p.ks);
-            if ((rows_per_cta + kMegaRows - 1 + rows_per_round - 1) / rows_per_round > 4) return no("tensor-parallel megakernel: more than 4 row rounds per CTA in a row-parallel phase");
-        }
-    }
+    if (!ok) return no("a weight matrix has K that is not a multiple of 256 (or an odd row count)");
+    // a warp's slice of a K window of the O projection (KS/8 elements) must lie inside one attention head
+    if (c->hd % (1 << (mega_ks_shift(c->qd_l) - 3)) != 0) return no("head_dim does not divide into the O projection's K windows");
     if (c->nkv_l > G) return no("more kv heads than SMs");
     c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
     if (const char* e = std::getenv("B2L_MEGA_NSPLIT")) c->mega_nsplit = std::max(1, std::min(c->mega_nsplit, std::atoi(e)));   // tuning knob
+    // the input vector as bf16 hi/mid/lo B fragments: 96 bytes per 16 elements; the attention scratch aliases that area
     const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
-    const size_t fixed = 8 * kMegaMaxStages * 2 + 64 + 64 + 128 + 4 * 2 * kMegaConsumerWarps * kMegaRows + sizeof(float) * kMegaXsFloats + 2 * static_cast<size_t>(c->H) + (48 + 8) * ph.size() + 16 + attn_scratch + 256;
+    const size_t xfrag = std::max(static_cast<size_t>(k_max) * 6, attn_scratch);
+    const size_t fixed = 8 * kMegaMaxStages * 2 + 16 + 64 + 64 + 4 * 2 * kMegaBatchGroups * kMegaConsumerWarps * 16 + (48 + 8) * ph.size() + 16 + xfrag + 256;
     int max_smem = 0;
     B2L_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->p.device));
+    if (static_cast<size_t>(max_smem) < fixed + 6 * static_cast<size_t>(kMegaStageBytes)) return no("not enough shared memory for the input fragments (K too large) and the weight ring");
     const int stages = std::min<int>(kMegaMaxStages, static_cast<int>((static_cast<size_t>(max_smem) - fixed) / kMegaStageBytes));
-    if (stages < 8) return no("not enough shared memory for the weight ring");
     c->mega_stages = stages;
     c->mega_smem = static_cast<size_t>(stages) * kMegaStageBytes + fixed;
-    if (const char* e = std::getenv("B2L_MEGA_LL")) c->mega_ll = std::atoi(e) != 0;
-    if (c->p.tp_size > 1) c->mega_ll = true;   // the tensor-parallel kernel exists in the dataflow build only
-    for (int v = 0; v < 3; v++) {
-        if ((v == 2) != (c->p.tp_size > 1)) continue;   // v 0/1: single-GPU kernel (barrier / dataflow build), v 2: tensor-parallel rank
-        void (*kern)() = v == 2 ? megatp::mega_decode_kernel<true> : v == 1 ? mega1::mega_decode_kernel<true> : mega1::mega_decode_kernel<false>;
+    {
+        MegaKernel kern = mega_kernel_for(c->hd, c->group, c->p.tp_size > 1);   // tensor-parallel rank / single GPU
         B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(c->mega_smem)));
         // the kernel calls non-inlined device functions: make sure the per-thread stack covers its frames
         cudaFuncAttributes fa{};
@@ -791,16 +813,26 @@ void mega_setup(b2l_ctx* c) {
             B2L_CUDA(cudaMemset(p, 0, words * sizeof(unsigned long long)));
             return p;
         };
-        c->mega_ll_h = zalloc((static_cast<size_t>(c->H) + 255) / 256 * 256);
+        c->mega_ll_h = zalloc(c->H);
         c->mega_ll_qkv = zalloc(c->qkv_l);
-        c->mega_ll_act = zalloc((static_cast<size_t>(c->I_l) + 255) / 256 * 256);
-        c->mega_ll_pacc = zalloc((n_part * c->hd + 255) / 256 * 256);   // ll_perm permutes within 256-word blocks
+        c->mega_ll_act = zalloc(c->I_l);
+        c->mega_ll_pacc = zalloc(n_part * c->hd);
         c->mega_ll_pml = zalloc(n_part * 2);
         c->mega_ll_keys = zalloc(static_cast<size_t>(2) * G);
         c->mega_seq = 0;
     }
-    c->mega_bar = dalloc<unsigned long long>(c, 8);
-    B2L_CUDA(cudaMemset(c->mega_bar, 0, sizeof(unsigned long long) * 8));
+    // the tiled weight images (a second copy of every matrix; the row-major one serves prefill and the multi-kernel path)
+    for (MegaPhase& p : ph) {
+        if (p.type == PH_ATTN) continue;
+        const size_t n = static_cast<size_t>(p.N) * p.K;
+        uint16_t* wt = dalloc<uint16_t>(c, n);
+        const long long pieces = static_cast<long long>(n / 8);
+        mega_tile_kernel<<<static_cast<unsigned>((pieces + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(p.W), reinterpret_cast<uint4*>(wt),
+                                                                                           p.N, p.K, p.type == PH_GATEUP ? 2 : 1, G);
+        B2L_CUDA(cudaGetLastError());
+        p.W = wt;
+    }
+    B2L_CUDA(cudaStreamSynchronize(c->stream));
     MegaPhase* d = dalloc<MegaPhase>(c, ph.size());
     B2L_CUDA(cudaMemcpy(d, ph.data(), sizeof(MegaPhase) * ph.size(), cudaMemcpyHostToDevice));
     c->mega_phases = d;
@@ -817,8 +849,6 @@ void mega_setup(b2l_ctx* c) {
         if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->mega_l2_persist_bytes = want;
         else cudaGetLastError();
     }
-    if (const char* e = std::getenv("B2L_MEGA_INFLIGHT")) c->mega_inflight = std::atoi(e);   // tuning knobs
-    if (const char* e = std::getenv("B2L_MEGA_L2AHEAD")) c->mega_l2_ahead = std::atoi(e);
     if (const char* e = std::getenv("B2L_MEGA_ATTN_TPS")) c->mega_attn_tps = std::max(16, std::atoi(e));
     if (const char* e = std::getenv("B2L_MEGA_STAGES")) c->mega_stages = std::max(2, std::min(c->mega_stages, std::atoi(e)));
     c->mega_ok = true;
@@ -837,11 +867,10 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
     a.embed = c->embed; a.rope = c->rope;
     a.H = c->H; a.V = c->V_l; a.nh = c->nh_l; a.nkv = c->nkv_l; a.hd = c->hd; a.I = c->I_l;
     a.eps = c->p.rms_norm_eps; a.attn_scale = 1.0f / sqrtf(static_cast<float>(c->hd));
-    a.h = c->h; a.qkv = c->qkv; a.attn = c->attn; a.act = c->act; a.logits = c->logits;
+    a.logits = c->logits;
     a.block_table = c->d_block_tables; a.page_size = c->p.page_size; a.kvd = c->kvd_l;
-    a.part_acc = c->part_acc; a.part_ml = c->part_ml; a.attn_counters = c->attn_counters; a.nsplit_max = c->mega_nsplit;
+    a.nsplit_max = c->mega_nsplit;
     a.token = c->d_tokens; a.position = c->d_positions; a.out_ids = c->d_out_ids; a.n_steps = n_steps;
-    a.bar_counter = c->mega_bar; a.bar_epoch = c->mega_bar + 1; a.argmax_keys = c->mega_bar + 2;
     a.ll_h = c->mega_ll_h; a.ll_qkv = c->mega_ll_qkv; a.ll_act = c->mega_ll_act; a.ll_pacc = c->mega_ll_pacc;
     a.ll_pml = c->mega_ll_pml; a.ll_keys = c->mega_ll_keys;
     a.seq_base = c->mega_seq;
@@ -856,8 +885,7 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
         a.tp_keys[0] = c->mega_ll_keys;
     }
     a.poll_sleep_ns = std::getenv("B2L_MEGA_POLL_NS") ? std::atoi(std::getenv("B2L_MEGA_POLL_NS")) : 0;
-    a.ll_use_sentinel = std::getenv("B2L_MEGA_SENTINEL") ? std::atoi(std::getenv("B2L_MEGA_SENTINEL")) : 0;
-    if (c->mega_ll) c->mega_seq += static_cast<uint32_t>(n_steps) * static_cast<uint32_t>(c->mega_n_phases);
+    c->mega_seq += static_cast<uint32_t>(n_steps) * static_cast<uint32_t>(c->mega_n_phases);
     int* dev_abort = nullptr;
     B2L_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_abort), c->mega_abort, 0));
     a.abort_flag = dev_abort;
@@ -872,10 +900,9 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
     a.prof = c->mega_prof;
     a.debug_progress = std::getenv("B2L_MEGA_DEBUG") ? 1 : 0;
     a.debug_nostream = std::getenv("B2L_MEGA_NOSTREAM") ? 1 : 0;
-    a.max_inflight = c->mega_inflight;
     a.attn_tps = c->mega_attn_tps;
+    a.l2_ahead = std::getenv("B2L_MEGA_L2AHEAD") ? std::atoi(std::getenv("B2L_MEGA_L2AHEAD")) : 8;   // measured: 8 chunks (19 MB chip-wide) -4.5 %, 32 chunks +9 % (L2 thrash)
     a.producer_sleep_ns = std::getenv("B2L_MEGA_PSLEEP") ? std::atoi(std::getenv("B2L_MEGA_PSLEEP")) : 100;
-    a.l2_ahead = c->mega_l2_ahead;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->prop.multiProcessorCount);
     cfg.blockDim = dim3(kMegaThreads);
@@ -896,14 +923,12 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
         attr[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.numAttrs = 2;
     }
-    if (!c->mega_ll) B2L_CUDA(cudaMemsetAsync(c->mega_bar + 2, 0, sizeof(unsigned long long) * 3, c->stream));   // argmax keys of the barrier build
     if (a.tp > 1) {
         B2L_CUDA(cudaMemcpyToSymbolAsync(megatp::c_mega, &a, sizeof(MegaArgs), 0, cudaMemcpyHostToDevice, c->stream));
-        B2L_CUDA(cudaLaunchKernelEx(&cfg, megatp::mega_decode_kernel<true>));
+        B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_kernel_for(c->hd, c->group, true)));
     } else {
         B2L_CUDA(cudaMemcpyToSymbolAsync(mega1::c_mega, &a, sizeof(MegaArgs), 0, cudaMemcpyHostToDevice, c->stream));
-        if (c->mega_ll) B2L_CUDA(cudaLaunchKernelEx(&cfg, mega1::mega_decode_kernel<true>));
-        else B2L_CUDA(cudaLaunchKernelEx(&cfg, mega1::mega_decode_kernel<false>));
+        B2L_CUDA(cudaLaunchKernelEx(&cfg, mega_kernel_for(c->hd, c->group, false)));
     }
     c->launched++;
 }

@@ -99,9 +99,7 @@ struct b2l_ctx {
     size_t mega_smem = 0;
     uint16_t* kv_base = nullptr;     // all layers' KV pools, contiguous
     size_t mega_l2_persist_bytes = 0;
-    int mega_inflight = 0, mega_l2_ahead = 0, mega_attn_tps = 128;
-    unsigned long long *mega_bar = nullptr;  // [0] counter, [1] epoch, [2..4] argmax keys (barrier build)
-    bool mega_ll = true;                     // dataflow build (B2L_MEGA_LL=0: the grid-barrier build, single GPU only)
+    int mega_attn_tps = 128;
     // dataflow mode: {value, seq} word buffers (h | qkv | act | attention partials | per-CTA argmax keys)
     unsigned long long *mega_ll_h = nullptr, *mega_ll_qkv = nullptr, *mega_ll_act = nullptr, *mega_ll_pacc = nullptr,
                        *mega_ll_pml = nullptr, *mega_ll_keys = nullptr;

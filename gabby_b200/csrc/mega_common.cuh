@@ -7,12 +7,13 @@ namespace b2l {
 
 constexpr int kMegaConsumerWarps = 8;
 constexpr int kMegaConsumerThreads = kMegaConsumerWarps * 32;
-constexpr int kMegaThreads = kMegaConsumerThreads + 32;  // + producer warp
+constexpr int kMegaThreads = kMegaConsumerThreads + 128;  // + the producer's warpgroup (one working lane; a whole warpgroup so
+                                                             // that setmaxnreg can hand its registers to the consumers)
 constexpr int kMegaStageBytes = 16 * 1024;
 constexpr int kMegaMaxStages = 12;
-constexpr int kMegaRows = 4;  // rows one warp reduces together (transposed butterfly)
-constexpr int kMegaXsFloats = 2048;
-constexpr int kMegaProfRows = 16 + 2 * 160;  // debug timeline: 16 summary rows, then per CTA: input-ready and phase-end times
+constexpr int kMegaGroupRows = 16;   // rows of one MMA tile (mma.sync.m16n8k16: the weights are the A operand)
+constexpr int kMegaBatchGroups = 8;  // row groups a CTA finishes per CTA barrier (128 rows: one reducing thread per row)
+constexpr int kMegaProfRows = 16 + 2 * 160 + 64;  // debug timeline: 16 summary rows, then per CTA: input-ready and phase-end times, then per warp of CTA 0: input ready / rows done
 
 enum MegaPhaseType { PH_QKV = 0, PH_ATTN = 1, PH_OPROJ = 2, PH_GATEUP = 3, PH_DOWN = 4, PH_LMHEAD = 5 };
 
@@ -22,12 +23,20 @@ struct MegaPhase {
     const uint16_t* norm_w;  // fused RMSNorm weight or null
     uint16_t* kv_pool;       // PH_ATTN: this layer's KV pool
     int N, K;
-    int ks;                  // warps per row (K split into ks slices of 256*m elements)
-    int m;                   // 16-byte sweeps per warp unit: slice = 256 * m elements (<= 2048)
+    int ks, m;               // unused (layout of the first version of the kernel)
 };
 
+// rows [r0, r1) of an N-row matrix owned by CTA `c` of `G` (unit = 2 rows for SwiGLU pairs)
+__host__ __device__ __forceinline__ void mega_row_range(int N, int unit, int c, int G, int& r0, int& r1) {
+    const long long units = N / unit;
+    r0 = static_cast<int>(units * c / G) * unit;
+    r1 = static_cast<int>(units * (c + 1) / G) * unit;
+}
+// K window of a ring stage: 512 elements, 256 when K is not a multiple of 512 (K % 256 == 0 is required)
+__host__ __device__ __forceinline__ int mega_ks_shift(int K) { return (K & 511) ? 8 : 9; }
+
 struct MegaArgs {
-    const MegaPhase* phases;
+    const MegaPhase* phases;   // W = the TILED image of the matrix (mega_tile_kernel)
     int n_phases;
     int n_stages;
     // model
@@ -35,13 +44,10 @@ struct MegaArgs {
     const float* rope;
     int H, V, nh, nkv, hd, I;
     float eps, attn_scale;
-    // activations (fp32, L2 resident)
-    float *h, *qkv, *attn, *act, *logits;
+    float* logits;   // [V] fp32 (parity tap and b2l_get_logits)
     // paged KV
     const int32_t* block_table;
     int page_size, kvd;
-    float *part_acc, *part_ml;
-    int* attn_counters;
     int nsplit_max;
     // token loop
     int32_t token0, pos0;  // arg_io != 0: first token / position travel in this struct (constant memory) instead of *token / *position
@@ -50,23 +56,17 @@ struct MegaArgs {
     int32_t* position;   // in: first position; out: advanced
     int32_t* out_ids;    // [n_steps]
     int n_steps;
-    // sync
-    unsigned long long* bar_counter;  // monotonically increasing arrivals
-    unsigned long long* bar_epoch;    // arrivals consumed by previous launches
-    unsigned long long* argmax_keys;  // [3]
     int* abort_flag;     // mapped pinned host memory: [0] abort code, [1 + cta] progress marker of each CTA (debug)
     int debug_nostream;  // 1: copy 16 bytes per chunk instead of the weights (timing experiments only; wrong results)
     int debug_progress;  // 1: CTAs record step*100000 + phase*100 + stage-of-phase
     int producer_sleep_ns;
     int attn_tps;       // context tokens per attention split (work item)
-    int max_inflight;   // bulk copies issued but not yet landed, per CTA (bounds queueing latency in L2/HBM)
-    int l2_ahead;       // chunks prefetched into L2 beyond the ring (0 = off)
+    int l2_ahead;       // chunks the producer prefetches into L2 beyond the ring while the ring is full (0 = off)
     // dataflow mode (kernel template LL): activations travel as 8-byte {fp32 bits, sequence number} words and every
     // reader polls for the sequence number of the phase that produces its input -- no grid barrier anywhere
     unsigned long long *ll_h, *ll_qkv, *ll_act, *ll_pacc, *ll_pml, *ll_keys;
     uint32_t seq_base;  // sequence numbers used by earlier launches
     int poll_sleep_ns;    // back-off between failed polls of the dataflow words
-    int ll_use_sentinel;  // 1: one lane per warp polls first, then everybody loads; 0: everybody polls its own words
     unsigned long long* prof;  // optional [9][n_phases + 1], see b2l_debug_mega_profile globaltimer ns of the LAST step (CTA 0 / CTA G-1: phase end, wait end)
     // tensor parallel (the MEGA_TP build of the kernel; tp == 1 otherwise): every rank runs the kernel on its shard. The
     // row-parallel phases (O-proj, down) store their partial sums as {value, seq} words straight into EVERY rank's slab over

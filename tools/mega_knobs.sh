@@ -1,6 +1,6 @@
 #!/bin/bash
 # Sweep the megakernel's tuning knobs (environment variables read at b2l_finalize / launch) on the headline bench.
-# usage: tools/mega_knobs.sh OUT.jsonl "B2L_MEGA_INFLIGHT=4" "B2L_MEGA_INFLIGHT=6 B2L_MEGA_STAGES=10" ...
+# usage: [B2L_LIB_PATH=...] tools/mega_knobs.sh OUT.jsonl "B2L_MEGA_L2AHEAD=16" "B2L_MEGA_L2AHEAD=32 B2L_MEGA_STAGES=8" ...
 out=$1; shift
 : > "$out"
 for kv in "" "$@"; do

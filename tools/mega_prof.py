@@ -71,3 +71,4 @@ for k in (0, 2, 3, 4, 5):
 sel = types == 1
 print("attention item breakdown, cta0 tid0 (us): q-rope / loads+scores / sub-slot merge / smem+barrier / CTA merge+store")
 print(" ".join(f"{ns[r][sel].mean()/1.965e3:6.2f}" for r in (9, 10, 11, 12, 13)))
+
