@@ -785,7 +785,7 @@ void mega_setup(b2l_ctx* c) {
     // the input vector as bf16 hi/mid/lo B fragments: 96 bytes per 16 elements; the attention scratch aliases that area
     const size_t attn_scratch = static_cast<size_t>(kMegaConsumerWarps) * c->group * (c->hd + 2) * sizeof(float);
     const size_t xfrag = std::max(static_cast<size_t>(k_max) * 6, attn_scratch);
-    const size_t fixed = 8 * kMegaMaxStages * 2 + 16 + 64 + 64 + 4 * 2 * kMegaBatchGroups * kMegaConsumerWarps * 16 + (48 + 8) * ph.size() + 16 + xfrag + 256;
+    const size_t fixed = 8 * kMegaMaxStages * 2 + 16 + 64 + 64 + 64 + 4 * 2 * kMegaBatchGroups * kMegaConsumerWarps * 16 + (48 + 8) * ph.size() + 16 + xfrag + 256;
     int max_smem = 0;
     B2L_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->p.device));
     if (static_cast<size_t>(max_smem) < fixed + 6 * static_cast<size_t>(kMegaStageBytes)) return no("not enough shared memory for the input fragments (K too large) and the weight ring");

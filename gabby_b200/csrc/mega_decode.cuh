@@ -36,8 +36,8 @@
 //   partials by attention (read by O-proj), act by gate/up (read by down), the per-CTA argmax keys by
 //   lm_head (read at the next token's first phase). Residual read-modify-writes of h touch only rows
 //   the same CTA owns in both O-proj and down.
-//   The only plain (non-word) data that crosses CTAs is the new token's K/V cache line: its
-//   writer fences before publishing its partials, readers fence once per token.
+//   The only plain (non-word) data that crosses CTAs is the new token's K/V cache line, first read by the
+//   next token: every CTA fences once per token before it publishes its argmax key, readers fence after the keys.
 //   Sequence numbers are 32 bits and never reset (host keeps seq_base across launches); buffers
 //   start at 0, which is never produced.
 //
@@ -150,6 +150,7 @@ struct MegaSmem {
     uint32_t ring;          // [n_stages][kMegaStageBytes]
     uint32_t full, empty;   // [n_stages] mbarriers each
     uint32_t zero16;        // 16 zero bytes: the `ldmatrix` row address of rows past the end of a group
+    uint32_t rel;           // [n_stages] u32: arrivals of finished readers per slot (2 per use; see the consumer wait)
     uint32_t keys;          // [8] u64
     uint32_t red;           // [2][8] fp32: per-warp sums of squares (double buffered by phase parity)
     uint32_t part;          // [2][kMegaBatchGroups][8 warps][16 rows] fp32 partial row sums (double buffered by batch)
@@ -188,10 +189,12 @@ __device__ __forceinline__ PhaseRegs mega_load_phase(uint32_t phases, int pi) {
 struct RingPos {
     int stage;
     uint32_t parity;
+    uint32_t use;   // how many times the ring has wrapped = earlier uses of slot `stage`
     __device__ __forceinline__ void advance(int n_stages) {
         if (++stage == n_stages) {
             stage = 0;
             parity ^= 1;
+            use++;
         }
     }
 };
@@ -303,22 +306,32 @@ __device__ __forceinline__ int mega_poll_token(const MegaSmem& sm, uint32_t want
     return argmax_key_index(best);
 }
 
-// NB K windows of this lane's slice of the input vector: fetch (poll the dataflow words, or read the embedding row), apply
-// the RMSNorm weight, accumulate the sum of squares, store the bf16 hi / mid / lo fragments. All NB loads are in flight together.
-template <int NB>
-__device__ __forceinline__ void mega_fetch_windows(const PhaseRegs& ph, const unsigned long long* src, const uint16_t* esrc, int kw0, bool from_embed,
-                                                   int p0, int P, int ks_shift, uint32_t want, bool poller, uint32_t frag0, uint32_t frag_window,
-                                                   float& ssq) {
+// Address of the B-fragment register that holds input elements (k, k+1), k even, in column 0 (hi): fragments are indexed by
+// k16-step (96 bytes: 12 lanes x 8 bytes); inside a step lane j = (k % 8) / 2 holds offsets 0..7 in b0 and 8..15 in b1.
+__device__ __forceinline__ uint32_t mega_frag_addr(uint32_t xfrag, int k) {
+    const int jj = (k & 15) >> 1;
+    return xfrag + ((k >> 4) * 12 + (jj & 3)) * 8 + ((jj >> 2) & 1) * 4;
+}
+
+// NB segments (64 consecutive input elements each: one 16-byte load per lane) of this warp's share of the input vector: fetch
+// (poll the dataflow words, or read the embedding row), apply the RMSNorm weight, accumulate the sum of squares, store the
+// bf16 hi / mid / lo fragments. All NB loads are in flight together. `seg_k(q)` = first element of segment q.
+template <int NB, typename SegK>
+__device__ __forceinline__ void mega_fetch_segments(const PhaseRegs& ph, const unsigned long long* src, const uint16_t* esrc, bool from_embed,
+                                                    int q0, int nseg, SegK seg_k, int lane, uint32_t want, uint32_t xfrag, float& ssq) {
     uint32_t nwv[NB];
     float x0[NB], x1[NB];
+    int k[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) k[j] = seg_k(min(q0 + j, nseg - 1)) + 2 * lane;   // segments past the end repeat the last one
     if (ph.norm_w) {   // RMSNorm weights of the slice: issued before the poll
 #pragma unroll
-        for (int j = 0; j < NB; j++) nwv[j] = ld_nc_early_u32(ph.norm_w + (min(p0 + j, P - 1) << ks_shift) + kw0);
+        for (int j = 0; j < NB; j++) nwv[j] = ld_nc_early_u32(ph.norm_w + k[j]);
     }
     if (from_embed) {
 #pragma unroll
         for (int j = 0; j < NB; j++) {
-            const uint32_t e = ld_nc_early_u32(esrc + (min(p0 + j, P - 1) << ks_shift));
+            const uint32_t e = ld_nc_early_u32(esrc + k[j]);
             x0[j] = bf16lo(e);
             x1[j] = bf16hi(e);
         }
@@ -327,7 +340,7 @@ __device__ __forceinline__ void mega_fetch_windows(const PhaseRegs& ph, const un
         for (;;) {
             uint4 wd[NB];
 #pragma unroll
-            for (int j = 0; j < NB; j++) wd[j] = ll_ld2(src + (min(p0 + j, P - 1) << ks_shift));
+            for (int j = 0; j < NB; j++) wd[j] = ll_ld2(src + k[j]);
             bool ok = true;
 #pragma unroll
             for (int j = 0; j < NB; j++) ok = ok && wd[j].y == want && wd[j].w == want;
@@ -345,29 +358,31 @@ __device__ __forceinline__ void mega_fetch_windows(const PhaseRegs& ph, const un
     }
 #pragma unroll
     for (int j = 0; j < NB; j++) {
-        if (p0 + j < P && poller) {
+        if (q0 + j < nseg) {
             float v0 = x0[j], v1 = x1[j];
             if (ph.norm_w) {
                 ssq = fmaf(v0, v0, fmaf(v1, v1, ssq));
                 v0 *= bf16lo(nwv[j]);
                 v1 *= bf16hi(nwv[j]);
             }
-            mega_put_frag(frag0 + (p0 + j) * frag_window, v0, v1);
+            mega_put_frag(mega_frag_addr(xfrag, k[j]), v0, v1);
         }
     }
 }
 
 // ---- one GEMV-type phase for one CTA ---------------------------------------------------------
-// Geometry of a phase with K input elements: KS = 512 (256 when K is not a multiple of 512) elements per K window,
-// P = K / KS windows per row group, T = KS / 128 k16-steps per warp per window. Warp w multiplies elements
-// [w*KS/8, (w+1)*KS/8) of every window; its slice of the input vector is what it polls, converts and keeps.
+// Geometry of a phase with K input elements: KS = 512 (256 when K is not a multiple of 512) elements per K window = ring
+// stage, P = K / KS windows per row group. The eight warps form four PAIRS; pair j owns the windows p = j, j+4, ... of every
+// group (four consecutive stages are in work at once, like four independent streams), and inside a window each warp of the
+// pair multiplies one half (KS/2 elements = T k16-steps). A warp polls, converts and keeps exactly the input elements it
+// multiplies; one wait and one arrive per warp per 8 KB of weights.
 __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaSmem& sm, ConsumerState& st_ref, int pi, int pos, int tid) {
     const MegaArgs& a = c_mega;
     ConsumerState& st = st_ref;
     const int lane = tid & 31, w = tid >> 5;
     const int K = ph.K, type = ph.type;
     const int ks_shift = (K & 511) ? 8 : 9;
-    const int P = K >> ks_shift, T = 1 << (ks_shift - 7);
+    const int P = K >> ks_shift;
     const bool prof = a.prof && st.step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
     unsigned long long* prof_col = a.prof + pi;
     const int prow = blockIdx.x == 0 ? 0 : 4, pstride = a.n_phases + 1;
@@ -375,6 +390,14 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
     volatile int* progress = a.debug_progress && tid == 0 ? a.abort_flag + 1 + blockIdx.x : nullptr;
     if (progress) *progress = st.step * 100000 + pi * 100 + 1;
 
+#ifdef MEGA_PROF_WARP
+    long long wt[8] = {clock64(), 0, 0, 0, 0, 0, 0, 0};   // debug: per-warp cycle stamps of the profiled step (CTA 0)
+#define MEGA_WT(i) wt[i] = clock64()
+#define MEGA_WT_ONCE(i) if (wt[i] == 0) wt[i] = clock64()
+#else
+#define MEGA_WT(i)
+#define MEGA_WT_ONCE(i)
+#endif
     const int r0 = ph.r0, r1 = ph.r1, nrows = r1 - r0;
     const bool from_embed = (type == PH_QKV && ph.layer == 0);
     const uint32_t gp = a.seq_base + static_cast<uint32_t>(st.step * a.n_phases + pi) + 1u;  // this phase's sequence number
@@ -388,39 +411,39 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
     if (progress) *progress = st.step * 100000 + pi * 100 + 2;
     const int token = st.token;
 
-    // ---- this warp's slice of the input vector -> bf16 hi / mid / lo B fragments in shared memory ----
-    // lane pl < 8T owns the element pair (k, k+1), k = p*KS + w*16T + 2*pl, of every window p (lanes past 8T, when
-    // T = 2, repeat the loads of lanes 0..15 and store nothing). Inside its k16-step t = pl / 8 the pair is B fragment
-    // register b0 (k offsets 0..7) or b1 (8..15) of fragment lane j = pl % 4.
-    const int pl = lane & (8 * T - 1);
-    const bool poller = lane < 8 * T;
-    const int kw0 = w * 16 * T + 2 * pl;
-    const uint32_t frag0 = sm.xfrag + ((w * T + (pl >> 3)) * 12 + (pl & 3)) * 8 + ((pl >> 2) & 1) * 4;   // + p * 8T * 96
-    const uint32_t frag_window = 8 * T * 96;
+    // ---- this warp's share of the input vector -> bf16 hi / mid / lo B fragments in shared memory ----
+    // The share is a list of 64-element segments: window m of the pair (p = pj + 4m) x this warp's half x LPW segments.
+    const int pj = w >> 1, ph_half = w & 1;
+    const int SL = 1 << (ks_shift - 1);                 // elements per warp per window
+    const int lpw_shift = ks_shift - 7;                 // log2(segments per warp per window): 2 or 1
+    const int nwin = pj < P ? (P - pj + 3) >> 2 : 0;
+    const int nseg = nwin << lpw_shift;
+    auto seg_k = [&](int q) { return ((pj + 4 * (q >> lpw_shift)) << ks_shift) + ph_half * SL + 64 * (q & ((1 << lpw_shift) - 1)); };
     float ssq = 0.f;
     if (type == PH_OPROJ) {
         // the attention phase left split-K partials (acc, max, sum) per (query head, split): merge them here
         const int nsplit = mega_attn_plan(a.nsplit_max, pos + 1, a.attn_tps, a.nh, gridDim.x).nsplit;
         const int group = a.nh / a.nkv;
-        for (int p0 = 0; p0 < P; p0 += 4) {
+        const int head_lane0 = a.hd >= 64 ? 0 : (lane & 16);   // a segment spans one head (two when head_dim is 32)
+        for (int q0 = 0; q0 < nseg; q0 += 4) {
             float Mx[4], L[4], acc0[4], acc1[4];
+            int kk[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { Mx[j] = -INFINITY; L[j] = 0.f; acc0[j] = 0.f; acc1[j] = 0.f; }
+            for (int j = 0; j < 4; j++) { Mx[j] = -INFINITY; L[j] = 0.f; acc0[j] = 0.f; acc1[j] = 0.f; kk[j] = seg_k(min(q0 + j, nseg - 1)) + 2 * lane; }
             for (int s0 = 0; s0 < nsplit; s0 += 4) {
                 uint4 wa[4][4], wm[4];
                 unsigned spins = 0;
                 for (;;) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const int k = (min(p0 + j, P - 1) << ks_shift) + kw0;       // windows past the end repeat the last one
-                        const int head = k / a.hd, d = k % a.hd;                    // a warp's slice of a window lies in one head
+                        const int head = kk[j] / a.hd, d = kk[j] % a.hd;
                         const size_t rbase = (static_cast<size_t>(head / group) * a.nsplit_max) * group + head % group;
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             const int sp = min(s0 + u, nsplit - 1);                 // clamped duplicates are masked below
                             wa[j][u] = ll_ld2(a.ll_pacc + (rbase + static_cast<size_t>(sp) * group) * a.hd + d);
                         }
-                        // (max, sum) of split s0 + u: fetched by lane u, handed round with shuffles
+                        // (max, sum) of split s0 + u: fetched by lane u of the head's lanes, handed round with shuffles
                         wm[j] = ll_ld2(a.ll_pml + (rbase + static_cast<size_t>(min(s0 + (lane & 3), nsplit - 1)) * group) * 2);
                     }
                     bool ok = true;
@@ -438,8 +461,8 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
                 for (int j = 0; j < 4; j++) {
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
-                        const float mu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].x), u);
-                        const float lu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].z), u);
+                        const float mu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].x), head_lane0 + u);
+                        const float lu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].z), head_lane0 + u);
                         if (s0 + u >= nsplit || mu == -INFINITY) continue;
                         const float mn = fmaxf(Mx[j], mu);
                         const float c_old = __expf(Mx[j] - mn), c_new = __expf(mu - mn);  // exp(-inf) = 0 on the first split
@@ -452,21 +475,21 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                if (p0 + j < P && poller) {
+                if (q0 + j < nseg) {
                     const float inv = 1.0f / L[j];
-                    mega_put_frag(frag0 + (p0 + j) * frag_window, acc0[j] * inv, acc1[j] * inv);
+                    mega_put_frag(mega_frag_addr(sm.xfrag, kk[j]), acc0[j] * inv, acc1[j] * inv);
                 }
             }
         }
     } else {
-        const unsigned long long* src = (type == PH_DOWN ? a.ll_act : a.ll_h) + kw0;
-        const uint16_t* esrc = a.embed + static_cast<size_t>(token) * a.H + kw0;
-        for (int p0 = 0; p0 < P;) {   // as many windows per round trip as fit the registers, without issuing duplicate loads
-            const int n = P - p0;
-            if (n >= 5) { mega_fetch_windows<8>(ph, src, esrc, kw0, from_embed, p0, P, ks_shift, want, poller, frag0, frag_window, ssq); p0 += 8; }
-            else if (n >= 3) { mega_fetch_windows<4>(ph, src, esrc, kw0, from_embed, p0, P, ks_shift, want, poller, frag0, frag_window, ssq); p0 += 4; }
-            else if (n == 2) { mega_fetch_windows<2>(ph, src, esrc, kw0, from_embed, p0, P, ks_shift, want, poller, frag0, frag_window, ssq); p0 += 2; }
-            else { mega_fetch_windows<1>(ph, src, esrc, kw0, from_embed, p0, P, ks_shift, want, poller, frag0, frag_window, ssq); p0 += 1; }
+        const unsigned long long* src = type == PH_DOWN ? a.ll_act : a.ll_h;
+        const uint16_t* esrc = a.embed + static_cast<size_t>(token) * a.H;
+        for (int q0 = 0; q0 < nseg;) {   // as many segments per round trip as fit the registers, without issuing duplicate loads
+            const int n = nseg - q0;
+            if (n >= 5) { mega_fetch_segments<8>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 8; }
+            else if (n >= 3) { mega_fetch_segments<4>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 4; }
+            else if (n == 2) { mega_fetch_segments<2>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 2; }
+            else { mega_fetch_segments<1>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 1; }
         }
         if (ph.norm_w) {
             ssq = warp_sum(ssq);
@@ -474,22 +497,23 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
         }
     }
     __syncwarp();   // the fragments are read by other lanes of this warp (never by other warps)
+    MEGA_WT(1);
     if (prof) prof_col[(prow + 2) * pstride] = globaltimer_ns();
     const bool prof_all = a.prof && st.step == a.n_steps - 1 && tid == 0 && blockIdx.x < 160;
     if (prof_all) prof_col[(16 + blockIdx.x) * pstride] = globaltimer_ns();
     if (progress) *progress = st.step * 100000 + pi * 100 + 3;
 
-    // ---- stream this CTA's rows: groups of <= 16 rows, P ring stages per group, every warp on its K slice ----
+    // ---- stream this CTA's rows: groups of <= 16 rows, P ring stages per group; this warp's pair takes every fourth stage ----
     const bool resid_h = type == PH_DOWN || (type == PH_OPROJ && ph.layer != 0);
     const bool resid_e = type == PH_OPROJ && ph.layer == 0;
     const int n_stages = a.n_stages;
     int* const abort_flag = a.abort_flag;
     unsigned long long best_key = st.best_key;
-    RingPos rp = st.rp;
+    RingPos rp = st.rp;   // first stage of the current group
+    const int T = 1 << (ks_shift - 5);   // k16-steps per warp per stage: 16 or 8
     // ldmatrix.x4: lanes 8i..8i+7 give the row addresses of 8x8 matrix i; matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
-    const uint32_t a_chunk0 = static_cast<uint32_t>(w * T * 2 + (lane >> 4));
-    const uint32_t bfrag = sm.xfrag + (w * T * 12 + lane) * 8;
+    const uint32_t a_piece0 = static_cast<uint32_t>(ph_half * T * 2 + (lane >> 4));
 #ifdef MEGA_PROF_ROUNDS
     long long pr_wait = 0, pr_math = 0, pr_tail = 0, pr_n = 0;
 #endif
@@ -506,50 +530,69 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
         for (int g = 0; g * 16 < brows; g++) {
             const int r = min(16, brows - g * 16);
             const bool rowok = a_row < r;
-            const uint32_t a_off = rowok ? (a_chunk0 * r + a_row) * 16 : 0u;
+            const uint32_t a_off = rowok ? (a_piece0 * r + a_row) * 16 : 0u;
             const uint32_t a_step = rowok ? static_cast<uint32_t>(r) * 32 : 0u;
-            // eight independent accumulators (k16-step t of even / odd windows): back-to-back MMAs into one accumulator would
-            // run at the tensor pipe's latency, not its rate
+            // eight independent accumulators: back-to-back MMAs into one accumulator would run at the tensor pipe's latency
             float c[8][4];
 #pragma unroll
             for (int i = 0; i < 8; i++) { c[i][0] = 0.f; c[i][1] = 0.f; c[i][2] = 0.f; c[i][3] = 0.f; }
-            uint32_t bf = bfrag;
-            auto stage = [&](int half) {
+            for (int p = pj; p < P; p += 4) {
+                // ring position of window p of this group
+                RingPos sp = rp;
+                sp.stage += p;
+                while (sp.stage >= n_stages) { sp.stage -= n_stages; sp.parity ^= 1; sp.use++; }
 #ifdef MEGA_PROF_ROUNDS
                 const long long t0 = clock64();
 #endif
-                mbar_wait(sm.full + rp.stage * 8, rp.parity, abort_flag, 200 + type);
+                MEGA_WT_ONCE(7);
+                {
+                    // Successive uses of a ring slot belong to different pairs, so a pair can get here before the PREVIOUS use of
+                    // the slot has even landed, and a parity wait cannot tell "one phase behind" from "done". The release counter
+                    // of the previous use is the proof that it landed (its readers finished); only then is the parity wait
+                    // unambiguous. (Usually satisfied on the first load.)
+                    unsigned spins = 0;
+                    for (;;) {
+                        uint32_t done;
+                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(sm.rel + sp.stage * 4) : "memory");
+                        if (static_cast<int32_t>(done - 2u * sp.use) >= 0) break;
+                        if (++spins > (1u << 28)) mega_die(abort_flag, 210 + type);
+                    }
+                }
+                mbar_wait(sm.full + sp.stage * 8, sp.parity, abort_flag, 200 + type);
+                MEGA_WT_ONCE(2);
 #ifdef MEGA_PROF_ROUNDS
                 const long long t1 = clock64();
 #endif
-                const uint32_t abase = rowok ? sm.ring + static_cast<uint32_t>(rp.stage) * kMegaStageBytes + a_off : sm.zero16;
-                uint32_t A[4][4];
-                uint2 B[4];
+                const uint32_t abase = rowok ? sm.ring + static_cast<uint32_t>(sp.stage) * kMegaStageBytes + a_off : sm.zero16;
+                const uint32_t bf = sm.xfrag + (((p << (ks_shift - 4)) + ph_half * T) * 12 + lane) * 8;
+                for (int t0 = 0; t0 < T; t0 += 8) {
+                    uint32_t A[8][4];
+                    uint2 B[8];
 #pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (t < T) ldmatrix_x4(A[t], abase + t * a_step);
+                    for (int t = 0; t < 8; t++) ldmatrix_x4(A[t], abase + (t0 + t) * a_step);
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    B[t] = make_uint2(0u, 0u);
-                    if (t < T && lane < 12) B[t] = lds64u2(bf + t * 96);
+                    for (int t = 0; t < 8; t++) {
+                        B[t] = make_uint2(0u, 0u);
+                        if (lane < 12) B[t] = lds64u2(bf + (t0 + t) * 96);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; t++) mma_bf16_16816(c[t], A[t], B[t].x, B[t].y);
                 }
-#pragma unroll
-                for (int t = 0; t < 4; t++)
-                    if (t < T) mma_bf16_16816(c[half * 4 + t], A[t], B[t].x, B[t].y);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(sm.empty + rp.stage * 8);   // kMegaConsumerWarps arrivals free the stage
-                rp.advance(n_stages);
-                bf += frag_window;
+                if (lane == 0) {
+                    // publish "this use was read" BEFORE arriving: the slot can only be refilled (and its next use released)
+                    // after both arrivals of this use, so the counter never runs backwards
+                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(sm.rel + sp.stage * 4) : "memory");
+                    mbar_arrive(sm.empty + sp.stage * 8);   // two arrivals (the pair) free the stage
+                }
 #ifdef MEGA_PROF_ROUNDS
                 pr_wait += t1 - t0; pr_math += clock64() - t1; pr_n++;
 #endif
-            };
-            int p = 0;
-            for (; p + 1 < P; p += 2) {
-                stage(0);
-                stage(1);
             }
-            if (p < P) stage(0);
+            MEGA_WT_ONCE(3);
+            // next group: P stages further
+            rp.stage += P;
+            while (rp.stage >= n_stages) { rp.stage -= n_stages; rp.parity ^= 1; rp.use++; }
             // C fragment: lane 4i + q holds columns 2q, 2q+1 of rows i (c[0], c[1]) and i + 8 (c[2], c[3]); columns 0, 1, 2 are
             // the hi, mid and lo products of the row
             float cs[4];
@@ -569,8 +612,10 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
 #ifdef MEGA_PROF_ROUNDS
         const long long t2 = clock64();
 #endif
+        if (b0 == 0) { MEGA_WT(4); }
         consumer_bar();   // every warp's K slice of every row of the batch is in shared memory
         st.batch++;
+        if (b0 == 0) { MEGA_WT(5); }
         if (tid < 16 * kMegaBatchGroups) {   // warps 0..3 finish the rows; warps 4..7 go on to the next batch / phase
             float s = 0.f;
 #pragma unroll
@@ -639,6 +684,15 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
         prof_col[12 * pstride] = pr_n;
     }
 #endif
+#ifdef MEGA_PROF_WARP
+    if (a.prof && st.step == a.n_steps - 1 && lane == 0 && blockIdx.x == 0) {
+        wt[6] = clock64();
+#pragma unroll
+        for (int i = 0; i < 8; i++) prof_col[(16 + 320 + i * 8 + w) * pstride] = static_cast<unsigned long long>(wt[i]);
+    }
+#endif
+#undef MEGA_WT
+#undef MEGA_WT_ONCE
     st.rp = rp;
     st.best_key = best_key;
     if (progress) *progress = st.step * 100000 + pi * 100 + 4;
@@ -663,13 +717,10 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
     const float* cs = a.rope + static_cast<size_t>(pos) * HD;  // [HALF][2]
     const int qd = a.nh * HD;
 
-    // rotate-half RoPE of one 8-wide slice of a head living in the fused qkv row (element offset `head`)
+    // rotate-half RoPE of one 8-wide slice of a head: xx[0..7] = elements j0r.. of the lower half, xx[8..15] = of the upper half
     const uint32_t want = gp - 1u;
-    auto rope_slice = [&](int head, float* out) {
-        const int d0 = sl * 8, j0r = d0 < HALF ? d0 : d0 - HALF;  // the slice lies in one half (HALF % 8 == 0)
-        float xx[16];
-        const unsigned long long* const pp[2] = {a.ll_qkv + head + j0r, a.ll_qkv + head + j0r + HALF};
-        ll_ld8n<2>(pp, want, xx, a.abort_flag, 180);
+    const int d0 = sl * 8, j0r = d0 < HALF ? d0 : d0 - HALF;  // the slice lies in one half (HALF % 8 == 0)
+    auto rope_apply = [&](const float* xx, float* out) {
         const float* x0 = xx;
         const float* x1 = xx + 8;
 #pragma unroll
@@ -678,6 +729,12 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
             out[i] = d0 < HALF ? x0[i] * c2.x - x1[i] * c2.y : x1[i] * c2.x + x0[i] * c2.y;
             out[i + 1] = d0 < HALF ? x0[i + 1] * c2.z - x1[i + 1] * c2.w : x1[i + 1] * c2.z + x0[i + 1] * c2.w;
         }
+    };
+    auto rope_slice = [&](int head, float* out) {   // head = element offset in the fused qkv row
+        float xx[16];
+        const unsigned long long* const pp[2] = {a.ll_qkv + head + j0r, a.ll_qkv + head + j0r + HALF};
+        ll_ld8n<2>(pp, want, xx, a.abort_flag, 180);
+        rope_apply(xx, out);
     };
     constexpr int U = 4;  // token slots per lane group in flight: all K/V loads of a block are issued before any math
     constexpr int STEP = U * kMegaConsumerWarps * TPW;
@@ -704,9 +761,31 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
     };
     load_block(j0);
     float q[GROUP][8];
+    // The item whose range ends at the token being decoded also needs that token's k and v (this step's projection): their
+    // words are polled together with the first query head (one round trip instead of three on the phase's critical path).
+    const bool has_new = j1 == ctx;
+    float k_new[8], v_new[8];
+    {
+        const int qh = (kvh * group_total + g0) * HD, kh = qd + kvh * HD;
+        if (has_new) {
+            float xx[40];
+            const unsigned long long* const pp[5] = {a.ll_qkv + qh + j0r, a.ll_qkv + qh + j0r + HALF, a.ll_qkv + kh + j0r, a.ll_qkv + kh + j0r + HALF,
+                                                     a.ll_qkv + qd + a.kvd + kvh * HD + sl * 8};
+            ll_ld8n<5>(pp, want, xx, a.abort_flag, 181);
+            rope_apply(xx, q[0]);
+            rope_apply(xx + 16, k_new);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v_new[i] = xx[32 + i];
+        } else {
+            rope_slice(qh, q[0]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { k_new[i] = 0.f; v_new[i] = 0.f; }
+        }
+    }
+#pragma unroll
+    for (int g = 1; g < GROUP; g++) rope_slice((kvh * group_total + g0 + g) * HD, q[g]);
 #pragma unroll
     for (int g = 0; g < GROUP; g++) {
-        rope_slice((kvh * group_total + g0 + g) * HD, q[g]);
 #pragma unroll
         for (int i = 0; i < 8; i++) q[g][i] *= a.attn_scale;
     }
@@ -728,18 +807,13 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
             valid[u] = j < j1;
             if (valid[u] && j == pos) {
                 // the token being decoded: K/V come from this step's projection; append them (bf16)
-                float kr[8];
-                rope_slice(qd + kvh * HD, kr);
-                float vv[8];
-                const unsigned long long* const pp[1] = {a.ll_qkv + qd + a.kvd + kvh * HD + sl * 8};
-                ll_ld8n<1>(pp, want, vv, a.abort_flag, 182);
-                kw[u] = make_uint4(pack_bf16x2(kr[0], kr[1]), pack_bf16x2(kr[2], kr[3]), pack_bf16x2(kr[4], kr[5]), pack_bf16x2(kr[6], kr[7]));
-                vw[u] = make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]), pack_bf16x2(vv[6], vv[7]));
-                if (g0 == 0) {  // one writer per kv head
+                kw[u] = make_uint4(pack_bf16x2(k_new[0], k_new[1]), pack_bf16x2(k_new[2], k_new[3]), pack_bf16x2(k_new[4], k_new[5]), pack_bf16x2(k_new[6], k_new[7]));
+                vw[u] = make_uint4(pack_bf16x2(v_new[0], v_new[1]), pack_bf16x2(v_new[2], v_new[3]), pack_bf16x2(v_new[4], v_new[5]), pack_bf16x2(v_new[6], v_new[7]));
+                if (g0 == 0) {  // one writer per kv head. No fence here: the line is first read by the NEXT token, and this
+                                // CTA fences once per token before it publishes its argmax key (readers fence after the keys)
                     const int page = __ldg(a.block_table + j / a.page_size), off = j % a.page_size;
                     *reinterpret_cast<uint4*>(kv.at(page, 0, off) + kvh * HD + sl * 8) = kw[u];
                     *reinterpret_cast<uint4*>(kv.at(page, 1, off) + kvh * HD + sl * 8) = vw[u];
-                    __threadfence();  // the cache line must be out before this item's partials announce the phase done
                 }
             }
         }
@@ -928,6 +1002,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     sm.full = p;  p += 8 * kMegaMaxStages;
     sm.empty = p; p += 8 * kMegaMaxStages;
     sm.zero16 = p; p += 16;
+    sm.rel = p;   p += 4 * 16;
     sm.keys = p;  p += 8 * 8;
     sm.red = p;   p += 4 * 16;
     sm.part = p;  p += 4 * 2 * kMegaBatchGroups * kMegaConsumerWarps * 16;
@@ -939,7 +1014,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; s++) {
             mbar_init(sm.full + s * 8, 1);
-            mbar_init(sm.empty + s * 8, kMegaConsumerWarps);
+            mbar_init(sm.empty + s * 8, 2);   // the two warps of the pair that reads the stage
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(sm.rel + s * 4), "r"(0u) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(sm.zero16), "r"(0u) : "memory");
@@ -979,7 +1055,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
             ld.seek_phase(sm.phases, a.n_phases, a.n_steps);
             pf.seek_phase(sm.phases, a.n_phases, a.n_steps);
             long long ld_index = 0, pf_index = 0;   // chunks issued to the ring / prefetched into L2
-            RingPos rp{0, 0};
+            RingPos rp{0, 0, 0};
             while (!ld.done(a.n_steps)) {
                 if (!mbar_test_wait(sm.empty + rp.stage * 8, rp.parity ^ 1)) {
                     // ring full: the consumers are in a latency-bound stretch (hand-off, attention) and HBM would idle. Use the
@@ -1022,7 +1098,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
     // ================= consumer warps =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     ConsumerState st;
-    st.rp = RingPos{0, 0};
+    st.rp = RingPos{0, 0, 0};
     st.best_key = 0ull;
     st.token = token0;
     st.step = 0;
@@ -1075,6 +1151,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                         k = o > k ? o : k;
                     }
                     const uint32_t gp = a.seq_base + static_cast<uint32_t>(step * a.n_phases + pi) + 1u;
+                    // the K/V cache lines this CTA appended during the token (plain stores, ordered before this thread by the CTA
+                    // barriers since) must be visible before the key announces the token done
+                    __threadfence();
 #if MEGA_TP
                     for (int p = 0; p < a.tp; p++)   // every rank takes the maximum over all ranks' CTAs itself
                         asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(a.tp_keys[p] + 2 * (a.tp_rank * gridDim.x + blockIdx.x)),

@@ -72,3 +72,16 @@ sel = types == 1
 print("attention item breakdown, cta0 tid0 (us): q-rope / loads+scores / sub-slot merge / smem+barrier / CTA merge+store")
 print(" ".join(f"{ns[r][sel].mean()/1.965e3:6.2f}" for r in (9, 10, 11, 12, 13)))
 
+
+# per warp of CTA 0 (builds with -DMEGA_PROF_WARP; cycle counter of its SM, 1.965 GHz): us after the warp entered the phase
+if ns.shape[0] >= 16 + 320 + 64 and ns[336:400].any():
+    labels = ["input ready", "1st stage landed", "1st group done", "rows done", "barrier passed", "phase left", "before 1st wait"]
+    for k in (0, 2, 3, 4, 5):
+        sel = types == k
+        if not sel.any():
+            continue
+        print(names[k])
+        base = ns[336:344][:, sel]
+        for i, lab in enumerate(labels):
+            v = ((ns[336 + 8 * (i + 1):344 + 8 * (i + 1)][:, sel] - base).mean(axis=1)) / 1.965e3
+            print(f"   {lab:18s} " + " ".join(f"{x:6.2f}" for x in v))
