@@ -175,11 +175,14 @@ class Tokenizer:
         _ck(lib().gb_tokenize(self.h, text.encode(), out.ctypes.data_as(C.c_void_p), out.size, C.byref(n)))
         return out[: n.value].tolist()
 
-    def detokenize(self, ids):
+    def detokenize_bytes(self, ids) -> bytes:
         a = np.ascontiguousarray(ids, np.int32)
         buf = C.create_string_buffer(16 * max(1, a.size) + 16)
         _ck(lib().gb_detokenize(self.h, a.ctypes.data_as(C.c_void_p), a.size, buf, len(buf)))
-        return buf.value.decode(errors="replace")
+        return buf.value
+
+    def detokenize(self, ids):
+        return self.detokenize_bytes(ids).decode(errors="replace")
 
     def chat_prompt(self, system: str, user: str):
         out = np.zeros(4 * (len(system.encode()) + len(user.encode())) + 64, np.int32)

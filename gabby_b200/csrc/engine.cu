@@ -760,7 +760,7 @@ void mega_setup(b2l_ctx* c) {
     int k_max = 0;
     auto add = [&](int type, int layer, const uint16_t* W, const uint16_t* norm, uint16_t* kv, int N, int K) -> bool {
         MegaPhase p{};
-        p.type = type; p.layer = layer; p.W = W; p.norm_w = norm; p.kv_pool = kv; p.N = N; p.K = K; p.ks = 0; p.m = 0;
+        p.type = type; p.layer = layer; p.W = W; p.norm_w = norm; p.kv_pool = kv; p.N = N; p.K = K; p.inv_k = K > 0 ? 1.0f / static_cast<float>(K) : 0.f; p.reserved = 0;
         if (type != PH_ATTN && (K % 256 != 0 || N % 2 != 0)) return false;
         k_max = std::max(k_max, K);
         ph.push_back(p);

@@ -23,7 +23,8 @@ struct MegaPhase {
     const uint16_t* norm_w;  // fused RMSNorm weight or null
     uint16_t* kv_pool;       // PH_ATTN: this layer's KV pool
     int N, K;
-    int ks, m;               // unused (layout of the first version of the kernel)
+    float inv_k;             // 1 / K (RMSNorm mean)
+    int reserved;
 };
 
 // rows [r0, r1) of an N-row matrix owned by CTA `c` of `G` (unit = 2 rows for SwiGLU pairs)

@@ -164,6 +164,7 @@ struct PhaseRegs {
     int type, layer, N, K;
     int r0, r1;              // this CTA's row range of the phase (precomputed once per launch)
     const uint16_t* W;       // tiled image of the matrix
+    float inv_k;             // 1 / K
     const uint16_t* norm_w;
     uint16_t* kv_pool;
 };
@@ -179,6 +180,7 @@ __device__ __forceinline__ PhaseRegs mega_load_phase(uint32_t phases, int pi) {
     r.kv_pool = reinterpret_cast<uint16_t*>(static_cast<unsigned long long>(a1.z) | (static_cast<unsigned long long>(a1.w) << 32));
     r.N = static_cast<int>(a2.x);
     r.K = static_cast<int>(a2.y);
+    r.inv_k = __uint_as_float(a2.z);
     unsigned long long rr = lds64(phases + c_mega.n_phases * 48 + pi * 8);
     r.r0 = static_cast<int>(rr & 0xffffffffull);
     r.r1 = static_cast<int>(rr >> 32);
@@ -411,9 +413,26 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
     if (progress) *progress = st.step * 100000 + pi * 100 + 2;
     const int token = st.token;
 
+    // ---- everything the row loop needs that does not depend on the input: computed (and the residual of the first batch
+    // fetched) BEFORE the input poll, so that it overlaps the wait instead of sitting on the critical path after it ----
+    const int pj = w >> 1, ph_half = w & 1;
+    const bool resid_h = type == PH_DOWN || (type == PH_OPROJ && ph.layer != 0);
+    const bool resid_e = type == PH_OPROJ && ph.layer == 0;
+    const int n_stages = a.n_stages;
+    int* const abort_flag = a.abort_flag;
+    RingPos rp = st.rp;   // first stage of the current group
+    const int T = 1 << (ks_shift - 5);   // k16-steps per warp per stage: 16 or 8
+    // ldmatrix.x4: lanes 8i..8i+7 give the row addresses of 8x8 matrix i; matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
+    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
+    const uint32_t a_piece0 = static_cast<uint32_t>(ph_half * T * 2 + (lane >> 4));
+    float resid0 = 0.f;
+    if (tid < min(16 * kMegaBatchGroups, nrows)) {
+        if (resid_h) resid0 = ld_cg_early_f32(a.ll_h + r0 + tid);
+        else if (resid_e) resid0 = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + r0 + tid]);
+    }
+
     // ---- this warp's share of the input vector -> bf16 hi / mid / lo B fragments in shared memory ----
     // The share is a list of 64-element segments: window m of the pair (p = pj + 4m) x this warp's half x LPW segments.
-    const int pj = w >> 1, ph_half = w & 1;
     const int SL = 1 << (ks_shift - 1);                 // elements per warp per window
     const int lpw_shift = ks_shift - 7;                 // log2(segments per warp per window): 2 or 1
     const int nwin = pj < P ? (P - pj + 3) >> 2 : 0;
@@ -504,16 +523,7 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
     if (progress) *progress = st.step * 100000 + pi * 100 + 3;
 
     // ---- stream this CTA's rows: groups of <= 16 rows, P ring stages per group; this warp's pair takes every fourth stage ----
-    const bool resid_h = type == PH_DOWN || (type == PH_OPROJ && ph.layer != 0);
-    const bool resid_e = type == PH_OPROJ && ph.layer == 0;
-    const int n_stages = a.n_stages;
-    int* const abort_flag = a.abort_flag;
     unsigned long long best_key = st.best_key;
-    RingPos rp = st.rp;   // first stage of the current group
-    const int T = 1 << (ks_shift - 5);   // k16-steps per warp per stage: 16 or 8
-    // ldmatrix.x4: lanes 8i..8i+7 give the row addresses of 8x8 matrix i; matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
-    const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
-    const uint32_t a_piece0 = static_cast<uint32_t>(ph_half * T * 2 + (lane >> 4));
 #ifdef MEGA_PROF_ROUNDS
     long long pr_wait = 0, pr_math = 0, pr_tail = 0, pr_n = 0;
 #endif
@@ -521,8 +531,8 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
         const int brows = min(16 * kMegaBatchGroups, nrows - b0);
         const int my_row = r0 + b0 + tid;
         const bool my_live = tid < brows;
-        float resid = 0.f;  // residual input of the row this thread will finish, fetched now so that its latency overlaps
-        if (my_live) {
+        float resid = resid0;  // residual input of the row this thread will finish (first batch: fetched before the input poll)
+        if (b0 > 0 && my_live) {
             if (resid_h) resid = ld_cg_early_f32(a.ll_h + my_row);
             else if (resid_e) resid = bf16_bits_to_f32(a.embed[static_cast<size_t>(token) * a.H + my_row]);
         }
@@ -624,7 +634,7 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
                 float ss = 0.f;
 #pragma unroll
                 for (int i = 0; i < kMegaConsumerWarps; i++) ss += lds32f(sm.red + ((pi & 1) * 8 + i) * 4);
-                s *= rsqrtf(ss * __frcp_rn(static_cast<float>(K)) + a.eps);
+                s *= rsqrtf(ss * ph.inv_k + a.eps);
             }
             if (type == PH_GATEUP) {
                 const float up = __shfl_down_sync(0xffffffffu, s, 1);  // rows are (gate, up) pairs
