@@ -33,8 +33,13 @@ __host__ __device__ __forceinline__ void mega_row_range(int N, int unit, int c, 
     r0 = static_cast<int>(units * c / G) * unit;
     r1 = static_cast<int>(units * (c + 1) / G) * unit;
 }
-// K window of a ring stage: 512 elements, 256 when K is not a multiple of 512 (K % 256 == 0 is required)
-__host__ __device__ __forceinline__ int mega_ks_shift(int K) { return (K & 511) ? 8 : 9; }
+// K window of a ring stage (log2 elements): 512 for the wide matrices; narrower for small K (the K shards of a tensor-parallel
+// rank: 512, 1024, 1792 ...) so that every group still has >= 4 windows, one for each warp pair. K % 128 == 0 is required.
+__host__ __device__ __forceinline__ int mega_ks_shift(int K) {
+    if ((K & 511) == 0 && K >= 2048) return 9;
+    if ((K & 255) == 0 && K >= 1024) return 8;
+    return 7;
+}
 
 struct MegaArgs {
     const MegaPhase* phases;   // W = the TILED image of the matrix (mega_tile_kernel)
@@ -62,6 +67,8 @@ struct MegaArgs {
     int debug_progress;  // 1: CTAs record step*100000 + phase*100 + stage-of-phase
     int producer_sleep_ns;
     int attn_tps;       // context tokens per attention split (work item)
+    int attn_max_splits;   // cap on context splits per head (every batch of 4 splits costs the O projection's input merge a round trip)
+    int attn_qhead_tokens; // per-query-head items (instead of per-kv-head items) while an item stays within this many tokens
     int l2_ahead;       // chunks the producer prefetches into L2 beyond the ring while the ring is full (0 = off)
     // dataflow mode (kernel template LL): activations travel as 8-byte {fp32 bits, sequence number} words and every
     // reader polls for the sequence number of the phase that produces its input -- no grid barrier anywhere

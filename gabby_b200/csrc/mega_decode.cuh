@@ -209,14 +209,16 @@ struct AttnPlan {
     bool per_q_head;
 };
 __device__ __forceinline__ AttnPlan mega_attn_plan(int nsplit_max, int ctx, int tps, int nh, int G) {
+    const MegaArgs& a = c_mega;
     AttnPlan p;
-    const int q_splits = min(nsplit_max, G / nh);          // splits per query head that still fit the grid
-    if (q_splits >= 1 && (ctx + q_splits - 1) / q_splits <= 2 * tps) {
-        p.per_q_head = true;                               // items of <= 2*tps tokens of ONE query head
+    const int cap = min(nsplit_max, a.attn_max_splits);
+    const int q_splits = min(cap, G / nh);          // splits per query head that still fit the grid
+    if (q_splits >= 1 && (ctx + q_splits - 1) / q_splits <= a.attn_qhead_tokens) {
+        p.per_q_head = true;                               // items of ONE query head
         p.nsplit = max(1, min(q_splits, (ctx + 31) / 32));
     } else {
         p.per_q_head = false;
-        p.nsplit = max(1, min(nsplit_max, (ctx + tps - 1) / tps));
+        p.nsplit = max(1, min(cap, (ctx + tps - 1) / tps));
     }
     return p;
 }
@@ -372,6 +374,69 @@ __device__ __forceinline__ void mega_fetch_segments(const PhaseRegs& ph, const u
     }
 }
 
+// O projection input: NS segments of this warp's share of the attention output, merged from the split-K partials the
+// attention items published (acc words per (head, split), max / sum words per (head, split)), NU splits per round trip.
+template <int NS, int NU, typename SegK>
+__device__ __forceinline__ void mega_merge_segments(int q0, int nseg, SegK seg_k, int lane, int nsplit, uint32_t want, uint32_t xfrag) {
+    const MegaArgs& a = c_mega;
+    const int group = a.nh / a.nkv;
+    const int head_lane0 = a.hd >= 64 ? 0 : (lane & 16);   // a segment spans one head (two when head_dim is 32)
+    float Mx[NS], L[NS], acc0[NS], acc1[NS];
+    int kk[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) { Mx[j] = -INFINITY; L[j] = 0.f; acc0[j] = 0.f; acc1[j] = 0.f; kk[j] = seg_k(min(q0 + j, nseg - 1)) + 2 * lane; }
+    for (int s0 = 0; s0 < nsplit; s0 += NU) {
+        uint4 wa[NS][NU], wm[NS];
+        unsigned spins = 0;
+        for (;;) {
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                const int head = kk[j] / a.hd, d = kk[j] % a.hd;
+                const size_t rbase = (static_cast<size_t>(head / group) * a.nsplit_max) * group + head % group;
+#pragma unroll
+                for (int u = 0; u < NU; u++) {
+                    const int sp = min(s0 + u, nsplit - 1);                 // clamped duplicates are masked below
+                    wa[j][u] = ll_ld2(a.ll_pacc + (rbase + static_cast<size_t>(sp) * group) * a.hd + d);
+                }
+                // (max, sum) of split s0 + u: fetched by lane u of the head's lanes, handed round with shuffles
+                wm[j] = ll_ld2(a.ll_pml + (rbase + static_cast<size_t>(min(s0 + (lane & (NU - 1)), nsplit - 1)) * group) * 2);
+            }
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                ok = ok && wm[j].y == want && wm[j].w == want;
+#pragma unroll
+                for (int u = 0; u < NU; u++) ok = ok && wa[j][u].y == want && wa[j][u].w == want;
+            }
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(c_mega.poll_sleep_ns);
+            if (++spins > (1u << 22)) mega_die(a.abort_flag, 120);
+        }
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const float mu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].x), head_lane0 + u);
+                const float lu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].z), head_lane0 + u);
+                if (s0 + u >= nsplit || mu == -INFINITY) continue;
+                const float mn = fmaxf(Mx[j], mu);
+                const float c_old = __expf(Mx[j] - mn), c_new = __expf(mu - mn);  // exp(-inf) = 0 on the first split
+                L[j] = L[j] * c_old + lu * c_new;
+                acc0[j] = acc0[j] * c_old + __uint_as_float(wa[j][u].x) * c_new;
+                acc1[j] = acc1[j] * c_old + __uint_as_float(wa[j][u].z) * c_new;
+                Mx[j] = mn;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NS; j++) {
+        if (q0 + j < nseg) {
+            const float inv = 1.0f / L[j];
+            mega_put_frag(mega_frag_addr(xfrag, kk[j]), acc0[j] * inv, acc1[j] * inv);
+        }
+    }
+}
+
 // ---- one GEMV-type phase for one CTA ---------------------------------------------------------
 // Geometry of a phase with K input elements: KS = 512 (256 when K is not a multiple of 512) elements per K window = ring
 // stage, P = K / KS windows per row group. The eight warps form four PAIRS; pair j owns the windows p = j, j+4, ... of every
@@ -383,7 +448,7 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
     ConsumerState& st = st_ref;
     const int lane = tid & 31, w = tid >> 5;
     const int K = ph.K, type = ph.type;
-    const int ks_shift = (K & 511) ? 8 : 9;
+    const int ks_shift = mega_ks_shift(K);
     const int P = K >> ks_shift;
     const bool prof = a.prof && st.step == a.n_steps - 1 && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
     unsigned long long* prof_col = a.prof + pi;
@@ -421,7 +486,7 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
     const int n_stages = a.n_stages;
     int* const abort_flag = a.abort_flag;
     RingPos rp = st.rp;   // first stage of the current group
-    const int T = 1 << (ks_shift - 5);   // k16-steps per warp per stage: 16 or 8
+    const int T = 1 << (ks_shift - 5);   // k16-steps per warp per stage: 16, 8 or 4
     // ldmatrix.x4: lanes 8i..8i+7 give the row addresses of 8x8 matrix i; matrices (rows 0-7 | 8-15) x (k 0-7 | 8-15)
     const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8;
     const uint32_t a_piece0 = static_cast<uint32_t>(ph_half * T * 2 + (lane >> 4));
@@ -440,65 +505,15 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
     auto seg_k = [&](int q) { return ((pj + 4 * (q >> lpw_shift)) << ks_shift) + ph_half * SL + 64 * (q & ((1 << lpw_shift) - 1)); };
     float ssq = 0.f;
     if (type == PH_OPROJ) {
-        // the attention phase left split-K partials (acc, max, sum) per (query head, split): merge them here
+        // the attention phase left split-K partials (acc, max, sum) per (query head, split): merge them here. About twenty
+        // 16-byte loads per lane per round trip: four segments x four splits, or fewer segments x more splits when the
+        // warp's share of a narrow K (a tensor-parallel rank's K shard) is only one or two segments
         const int nsplit = mega_attn_plan(a.nsplit_max, pos + 1, a.attn_tps, a.nh, gridDim.x).nsplit;
-        const int group = a.nh / a.nkv;
-        const int head_lane0 = a.hd >= 64 ? 0 : (lane & 16);   // a segment spans one head (two when head_dim is 32)
-        for (int q0 = 0; q0 < nseg; q0 += 4) {
-            float Mx[4], L[4], acc0[4], acc1[4];
-            int kk[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) { Mx[j] = -INFINITY; L[j] = 0.f; acc0[j] = 0.f; acc1[j] = 0.f; kk[j] = seg_k(min(q0 + j, nseg - 1)) + 2 * lane; }
-            for (int s0 = 0; s0 < nsplit; s0 += 4) {
-                uint4 wa[4][4], wm[4];
-                unsigned spins = 0;
-                for (;;) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int head = kk[j] / a.hd, d = kk[j] % a.hd;
-                        const size_t rbase = (static_cast<size_t>(head / group) * a.nsplit_max) * group + head % group;
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int sp = min(s0 + u, nsplit - 1);                 // clamped duplicates are masked below
-                            wa[j][u] = ll_ld2(a.ll_pacc + (rbase + static_cast<size_t>(sp) * group) * a.hd + d);
-                        }
-                        // (max, sum) of split s0 + u: fetched by lane u of the head's lanes, handed round with shuffles
-                        wm[j] = ll_ld2(a.ll_pml + (rbase + static_cast<size_t>(min(s0 + (lane & 3), nsplit - 1)) * group) * 2);
-                    }
-                    bool ok = true;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        ok = ok && wm[j].y == want && wm[j].w == want;
-#pragma unroll
-                        for (int u = 0; u < 4; u++) ok = ok && wa[j][u].y == want && wa[j][u].w == want;
-                    }
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    __nanosleep(c_mega.poll_sleep_ns);
-                    if (++spins > (1u << 22)) mega_die(a.abort_flag, 120);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const float mu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].x), head_lane0 + u);
-                        const float lu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].z), head_lane0 + u);
-                        if (s0 + u >= nsplit || mu == -INFINITY) continue;
-                        const float mn = fmaxf(Mx[j], mu);
-                        const float c_old = __expf(Mx[j] - mn), c_new = __expf(mu - mn);  // exp(-inf) = 0 on the first split
-                        L[j] = L[j] * c_old + lu * c_new;
-                        acc0[j] = acc0[j] * c_old + __uint_as_float(wa[j][u].x) * c_new;
-                        acc1[j] = acc1[j] * c_old + __uint_as_float(wa[j][u].z) * c_new;
-                        Mx[j] = mn;
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (q0 + j < nseg) {
-                    const float inv = 1.0f / L[j];
-                    mega_put_frag(mega_frag_addr(sm.xfrag, kk[j]), acc0[j] * inv, acc1[j] * inv);
-                }
-            }
+        for (int q0 = 0; q0 < nseg;) {
+            const int n = nseg - q0;
+            if (n >= 3) { mega_merge_segments<4, 4>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 4; }
+            else if (n == 2) { mega_merge_segments<2, 8>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 2; }
+            else { mega_merge_segments<1, 16>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 1; }
         }
     } else {
         const unsigned long long* src = type == PH_DOWN ? a.ll_act : a.ll_h;
@@ -575,18 +590,32 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
 #endif
                 const uint32_t abase = rowok ? sm.ring + static_cast<uint32_t>(sp.stage) * kMegaStageBytes + a_off : sm.zero16;
                 const uint32_t bf = sm.xfrag + (((p << (ks_shift - 4)) + ph_half * T) * 12 + lane) * 8;
-                for (int t0 = 0; t0 < T; t0 += 8) {
-                    uint32_t A[8][4];
-                    uint2 B[8];
+                if (T >= 8) {
+                    for (int t0 = 0; t0 < T; t0 += 8) {   // eight independent MMAs per round of loads
+                        uint32_t A[8][4];
+                        uint2 B[8];
 #pragma unroll
-                    for (int t = 0; t < 8; t++) ldmatrix_x4(A[t], abase + (t0 + t) * a_step);
+                        for (int t = 0; t < 8; t++) ldmatrix_x4(A[t], abase + (t0 + t) * a_step);
 #pragma unroll
-                    for (int t = 0; t < 8; t++) {
+                        for (int t = 0; t < 8; t++) {
+                            B[t] = make_uint2(0u, 0u);
+                            if (lane < 12) B[t] = lds64u2(bf + (t0 + t) * 96);
+                        }
+#pragma unroll
+                        for (int t = 0; t < 8; t++) mma_bf16_16816(c[t], A[t], B[t].x, B[t].y);
+                    }
+                } else {   // T = 4: the 128-element windows of a narrow K
+                    uint32_t A[4][4];
+                    uint2 B[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) ldmatrix_x4(A[t], abase + t * a_step);
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
                         B[t] = make_uint2(0u, 0u);
-                        if (lane < 12) B[t] = lds64u2(bf + (t0 + t) * 96);
+                        if (lane < 12) B[t] = lds64u2(bf + t * 96);
                     }
 #pragma unroll
-                    for (int t = 0; t < 8; t++) mma_bf16_16816(c[t], A[t], B[t].x, B[t].y);
+                    for (int t = 0; t < 4; t++) mma_bf16_16816(c[t], A[t], B[t].x, B[t].y);
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -748,9 +777,9 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
     };
     constexpr int U = 4;  // token slots per lane group in flight: all K/V loads of a block are issued before any math
     constexpr int STEP = U * kMegaConsumerWarps * TPW;
-    uint4 kw[U], vw[U];
+    uint4 kwA[U], vwA[U];
     // cached tokens do not depend on this step's projections: their K/V loads go out BEFORE the wait for q
-    auto load_block = [&](int jb) {
+    auto load_block = [&](uint4 (&kw)[U], uint4 (&vw)[U], int jb) {
         int page[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -769,7 +798,7 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
             }
         }
     };
-    load_block(j0);
+    load_block(kwA, vwA, j0);
     float q[GROUP][8];
     // The item whose range ends at the token being decoded also needs that token's k and v (this step's projection): their
     // words are polled together with the first query head (one round trip instead of three on the phase's critical path).
@@ -808,8 +837,7 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
 #pragma unroll
         for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
     }
-    for (int jb = j0; jb < j1; jb += STEP) {
-        if (jb != j0) load_block(jb);
+    auto block = [&](uint4 (&kw)[U], uint4 (&vw)[U], int jb) {
         bool valid[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -872,6 +900,27 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
                 for (int i = 0; i < 8; i++) acc[g][i] = fmaf(pu[u], vf[i], acc[g][i]);
             }
             m[g] = mn;
+        }
+    };
+    // Two blocks of K/V in flight (block i+1 loads while block i is computed) for per-query-head items at head_dim 128, where a
+    // block is 64 tokens and long contexts make items of many blocks (8B TP=8 rank shapes at context 4096: attention phase
+    // 19.9 -> 11.1 us). At head_dim 64 a block is 128 tokens, short-context items are one or two blocks, and the extra code
+    // cost the 1B headline 1.6 %.
+    if constexpr (GROUP == 1 && HD >= 128) {
+        uint4 kwB[U], vwB[U];
+        for (int jb = j0; jb < j1; jb += 2 * STEP) {
+            const bool more = jb + STEP < j1;
+            if (more) load_block(kwB, vwB, jb + STEP);
+            block(kwA, vwA, jb);
+            if (more) {
+                if (jb + 2 * STEP < j1) load_block(kwA, vwA, jb + 2 * STEP);
+                block(kwB, vwB, jb + STEP);
+            }
+        }
+    } else {   // (the whole-group item has no registers to spare for a second block)
+        for (int jb = j0; jb < j1; jb += STEP) {
+            if (jb != j0) load_block(kwA, vwA, jb);
+            block(kwA, vwA, jb);
         }
     }
     if (pcol) ak2 = clock64();
@@ -973,7 +1022,7 @@ struct ChunkCursor {
                 row = ph.r0;
                 r1 = ph.r1;
                 K = ph.K;
-                ks_shift = (K & 511) ? 8 : 9;
+                ks_shift = mega_ks_shift(K);
                 P = K >> ks_shift;
                 s = 0;
                 W = ph.W;

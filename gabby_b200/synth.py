@@ -64,6 +64,9 @@ PRESETS = {
     "3b": LlamaArch(3072, 8192, 28, 24, 8, 128, 128256, True),
     "8b": LlamaArch(4096, 14336, 32, 32, 8, 128, 128256, False, rope_factor=8.0),
     "70b": LlamaArch(8192, 28672, 80, 64, 8, 128, 128256, False, rope_factor=8.0),
+    # the per-rank shapes of Llama-3.1-8B at TP=8 as a single-GPU model (4 query heads on 1 kv head, I/8, V/8): a one-GPU proxy
+    # for tuning the phases of a tensor-parallel rank (tools/tp_proxy_bench.py); not a real model
+    "8b_tp8rank": LlamaArch(4096, 1792, 32, 4, 1, 128, 16032, False, rope_factor=8.0),
 }
 
 
