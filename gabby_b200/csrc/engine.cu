@@ -601,13 +601,24 @@ void prefill_gemm(b2l_ctx* c, int T, int n_seq, int tap_row0) {
             // flash-style causal attention over the paged cache, tensor-core S and PV, bf16 output
             FlashArgs fa{c->pf_qkv, c->qkv_l, kv, c->d_block_tables, c->max_blocks_cap, static_cast<const PrefillTile*>(c->pf_tiles),
                          c->pf_attn16, c->qd_l, c->group, scale * 1.4426950408889634f};
-            const dim3 grid(c->pf_n_tiles, c->nh_l);
-            // shared memory: the Q tile + two {K, V} buffers of 64 padded rows each
-            const size_t fsmem = static_cast<size_t>(5) * 64 * (c->hd + 8) * 2;
-            ensure_smem_optin(reinterpret_cast<const void*>(flash_prefill_kernel<64>), c->p.device, 5 * 64 * (64 + 8) * 2);
-            ensure_smem_optin(reinterpret_cast<const void*>(flash_prefill_kernel<128>), c->p.device, 5 * 64 * (128 + 8) * 2);
-            if (c->hd == 64) flash_prefill_kernel<64><<<grid, kFlashThreads, fsmem, c->stream>>>(fa);
-            else flash_prefill_kernel<128><<<grid, kFlashThreads, fsmem, c->stream>>>(fa);
+            // GH query heads of one kv head per CTA share the K/V tiles; shared memory: two {K, V} buffers of 64 padded rows each
+            const int gh = flash_heads_per_cta(c->hd, c->group);
+            const dim3 grid(c->pf_n_tiles, c->nh_l / gh);
+            const size_t fsmem = static_cast<size_t>(4) * 64 * (c->hd + 8) * 2;
+            auto go = [&](auto kern) {
+                ensure_smem_optin(reinterpret_cast<const void*>(kern), c->p.device, static_cast<int>(fsmem));
+                kern<<<grid, kFlashThreads * gh, fsmem, c->stream>>>(fa);
+            };
+            if (c->hd == 64) {
+                if (gh == 4) go(flash_prefill_kernel<64, 4>);
+                else if (gh == 3) go(flash_prefill_kernel<64, 3>);
+                else if (gh == 2) go(flash_prefill_kernel<64, 2>);
+                else go(flash_prefill_kernel<64, 1>);
+            } else {
+                if (gh == 3) go(flash_prefill_kernel<128, 3>);
+                else if (gh == 2) go(flash_prefill_kernel<128, 2>);
+                else go(flash_prefill_kernel<128, 1>);
+            }
             B2L_CUDA(cudaGetLastError());
             c->launched++;
         } else {

@@ -1,9 +1,9 @@
 // flash_prefill.cuh -- causal GQA attention for prefill, flash-style (online softmax, no S x S matrix),
-// over the paged bf16 KV cache. One CTA = 64 consecutive query positions of one sequence x one query
-// head; 4 warps x 16 query rows. K/V tiles of 64 tokens are gathered page by page into shared memory
-// with cp.async, S = Q K^T and O += P V run on the tensor cores (mma.sync m16n8k16 bf16, fp32
-// accumulate: the warp-level path is enough here -- attention is ~6 % of the prefill FLOPs and is
-// bounded by the K/V gather, the GEMMs are the tcgen05 kernels).
+// over the paged bf16 KV cache. One CTA = 64 consecutive query positions of one sequence x GH query
+// heads that share a kv head (GH = 3 for Llama-3.2-3B's group of 3): 4 x GH warps, each 16 query rows of
+// one head, all reading the SAME K/V tiles -- the tiles of 64 tokens are gathered page by page into shared
+// memory with cp.async once per group instead of once per query head. S = Q K^T and O += P V run on the
+// tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate).
 //   q: fp32 [T][ld] already rotated (rope_kv_kernel), rounded to bf16 on load
 //   out: bf16 [T][ldo] (the A operand of the O-projection GEMM)
 // Math = oracle attention with ORC_KV_BF16 | ORC_QP_BF16 (P rounded to bf16 before P V).
@@ -33,7 +33,7 @@ struct FlashArgs {
     float scale_log2e;
 };
 
-constexpr int kFlashBM = 64, kFlashBN = 64, kFlashThreads = 128;
+constexpr int kFlashBM = 64, kFlashBN = 64, kFlashThreads = 128;   // threads per query head of a CTA
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -50,33 +50,45 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int HD>
-__global__ void __launch_bounds__(kFlashThreads) flash_prefill_kernel(const FlashArgs a) {
+// heads per CTA: the largest divisor of the group that the register file allows (head_dim 128: 3 x 128 threads x ~170 registers)
+__host__ __device__ constexpr int flash_heads_per_cta(int hd, int group) {
+    const int cap = hd >= 128 ? 3 : 4;
+    for (int g = cap; g > 1; g--)
+        if (group % g == 0) return g;
+    return 1;
+}
+
+template <int HD, int GH>
+__global__ void __launch_bounds__(kFlashThreads * GH) flash_prefill_kernel(const FlashArgs a) {
     constexpr int LDS = HD + 8;           // padded row (bf16 elements): 16-byte shift per row kills ldmatrix bank conflicts
     constexpr int KSTEPS = HD / 16;       // k-steps of Q K^T
     constexpr int DBLOCKS = HD / 8;       // 8-wide output column blocks
     extern __shared__ __align__(16) uint16_t fsm[];
-    uint16_t* sQ = fsm;                        // [64][LDS]
-    uint16_t* sKV = sQ + kFlashBM * LDS;       // two buffers of {K [64][LDS], V [64][LDS]}: tile i+1 loads while tile i computes
+    uint16_t* sKV = fsm;                       // two buffers of {K [64][LDS], V [64][LDS]}: tile i+1 loads while tile i computes
+    uint16_t* sQ = fsm;                        // [GH][64][LDS] staged in the same memory before the first K/V tile is issued
+    static_assert(GH <= 4, "the Q tiles of the CTA's heads are staged in the K/V buffers");
     const PrefillTile tile = a.tiles[blockIdx.x];
-    const int head = blockIdx.y, kvh = head / a.group;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int tid = threadIdx.x, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+    const int hg = (tid >> 5) / 4, warp = (tid >> 5) % 4;        // head within the CTA, 16-row block within the tile
+    const int head0 = blockIdx.y * GH, head = head0 + hg, kvh = head0 / a.group;
+    constexpr int kThreads = kFlashThreads * GH;
     const int32_t* bt = a.block_tables + static_cast<size_t>(tile.slot) * a.max_blocks;
 
     // ---- Q tile: fp32 (rotated) -> bf16 in shared memory; rows past the tile repeat the last row ----
-    for (int i = tid; i < kFlashBM * (HD / 4); i += kFlashThreads) {
-        const int r = i / (HD / 4), c = (i % (HD / 4)) * 4;
+    for (int i = tid; i < GH * kFlashBM * (HD / 4); i += kThreads) {
+        const int h = i / (kFlashBM * (HD / 4)), r = (i / (HD / 4)) % kFlashBM, c = (i % (HD / 4)) * 4;
         const int row = tile.row0 + min(r, tile.n_rows - 1);
-        const float4 v = *reinterpret_cast<const float4*>(a.qkv + static_cast<size_t>(row) * a.ld + head * HD + c);
-        *reinterpret_cast<uint2*>(sQ + r * LDS + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        const float4 v = *reinterpret_cast<const float4*>(a.qkv + static_cast<size_t>(row) * a.ld + (head0 + h) * HD + c);
+        *reinterpret_cast<uint2*>(sQ + (h * kFlashBM + r) * LDS + c) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
     __syncthreads();
     uint32_t qf[KSTEPS][4];
     {
         const int mat = lane >> 3, r = (lane & 7) + (mat & 1) * 8, c = (mat >> 1) * 8;
 #pragma unroll
-        for (int kk = 0; kk < KSTEPS; kk++) ldmatrix_x4(smem_u32(sQ + (warp * 16 + r) * LDS + kk * 16 + c), qf[kk]);
+        for (int kk = 0; kk < KSTEPS; kk++) ldmatrix_x4(smem_u32(sQ + (hg * kFlashBM + warp * 16 + r) * LDS + kk * 16 + c), qf[kk]);
     }
+    __syncthreads();   // the Q staging area becomes the K/V buffers
     float o[DBLOCKS][4];
 #pragma unroll
     for (int d = 0; d < DBLOCKS; d++) o[d][0] = o[d][1] = o[d][2] = o[d][3] = 0.f;
@@ -88,7 +100,7 @@ __global__ void __launch_bounds__(kFlashThreads) flash_prefill_kernel(const Flas
     auto issue_tile = [&](int j0, int buf) {
         uint16_t* sK = sKV + buf * 2 * kFlashBN * LDS;
         uint16_t* sV = sK + kFlashBN * LDS;
-        for (int i = tid; i < kFlashBN * (HD / 8); i += kFlashThreads) {
+        for (int i = tid; i < kFlashBN * (HD / 8); i += kThreads) {
             const int r = i / (HD / 8), c = (i % (HD / 8)) * 8;
             const int j = min(j0 + r, kv_end - 1);
             const int page = bt[j / a.kv.page_size], off = j % a.kv.page_size;
