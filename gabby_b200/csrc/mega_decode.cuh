@@ -520,7 +520,8 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
         const uint16_t* esrc = a.embed + static_cast<size_t>(token) * a.H;
         for (int q0 = 0; q0 < nseg;) {   // as many segments per round trip as fit the registers, without issuing duplicate loads
             const int n = nseg - q0;
-            if (n >= 5) { mega_fetch_segments<8>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 8; }
+            if (n >= 9) { mega_fetch_segments<16>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 16; }
+            else if (n >= 5) { mega_fetch_segments<8>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 8; }
             else if (n >= 3) { mega_fetch_segments<4>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 4; }
             else if (n == 2) { mega_fetch_segments<2>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 2; }
             else { mega_fetch_segments<1>(ph, src, esrc, from_embed, q0, nseg, seg_k, lane, want, sm.xfrag, ssq); q0 += 1; }
@@ -775,7 +776,9 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
         ll_ld8n<2>(pp, want, xx, a.abort_flag, 180);
         rope_apply(xx, out);
     };
-    constexpr int U = 4;  // token slots per lane group in flight: all K/V loads of a block are issued before any math
+    // token slots per lane group in flight: all K/V loads of a block are issued before any math. Six at head_dim 64 for the
+    // per-query-head items (a block = 192 tokens: the items of contexts up to 768 are ONE block, no second round trip to L2)
+    constexpr int U = HD == 64 && GROUP == 1 ? 6 : 4;
     constexpr int STEP = U * kMegaConsumerWarps * TPW;
     uint4 kwA[U], vwA[U];
     // cached tokens do not depend on this step's projections: their K/V loads go out BEFORE the wait for q
