@@ -789,6 +789,7 @@ void mega_setup(b2l_ctx* c) {
     ok = ok && add(PH_LMHEAD, c->L, c->lm_head, c->final_norm, nullptr, c->V_l, c->H);
     if (!ok) return no("a weight matrix has K that is not a multiple of 128 (or an odd row count)");
     if (c->nkv_l > G) return no("more kv heads than SMs");
+    if ((c->p.page_size & (c->p.page_size - 1)) != 0) return no("KV page size is not a power of two");
     c->mega_nsplit = std::max(1, std::min(c->nsplit, G / c->nkv_l));
     if (const char* e = std::getenv("B2L_MEGA_NSPLIT")) c->mega_nsplit = std::max(1, std::min(c->mega_nsplit, std::atoi(e)));   // tuning knob
     // the input vector as bf16 hi/mid/lo B fragments: 96 bytes per 16 elements; the attention scratch aliases that area
@@ -878,6 +879,8 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
     a.eps = c->p.rms_norm_eps; a.attn_scale = 1.0f / sqrtf(static_cast<float>(c->hd));
     a.logits = c->logits;
     a.block_table = c->d_block_tables; a.page_size = c->p.page_size; a.kvd = c->kvd_l;
+    a.page_shift = 0;
+    while ((1 << a.page_shift) < a.page_size) a.page_shift++;
     a.nsplit_max = c->mega_nsplit;
     a.token = c->d_tokens; a.position = c->d_positions; a.out_ids = c->d_out_ids; a.n_steps = n_steps;
     a.ll_h = c->mega_ll_h; a.ll_qkv = c->mega_ll_qkv; a.ll_act = c->mega_ll_act; a.ll_pacc = c->mega_ll_pacc;

@@ -53,7 +53,7 @@ struct MegaArgs {
     float* logits;   // [V] fp32 (parity tap and b2l_get_logits)
     // paged KV
     const int32_t* block_table;
-    int page_size, kvd;
+    int page_size, page_shift, kvd;   // page_size is a power of two (2^page_shift)
     int nsplit_max;
     // token loop
     int32_t token0, pos0;  // arg_io != 0: first token / position travel in this struct (constant memory) instead of *token / *position

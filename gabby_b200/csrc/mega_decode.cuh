@@ -86,6 +86,8 @@ __device__ __forceinline__ uint32_t ld_nc_early_u32(const void* p) {
     return r;
 }
 
+template <int V> struct IntTag { static constexpr int value = V; };
+
 // ---- dataflow words: {value, seq} in one 8-byte store; a 16-byte load brings two adjacent words ----
 __device__ __forceinline__ void ll_st(unsigned long long* p, float v, uint32_t seq) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"((static_cast<unsigned long long>(seq) << 32) | __float_as_uint(v)) : "memory");
@@ -376,30 +378,36 @@ __device__ __forceinline__ void mega_fetch_segments(const PhaseRegs& ph, const u
 
 // O projection input: NS segments of this warp's share of the attention output, merged from the split-K partials the
 // attention items published (acc words per (head, split), max / sum words per (head, split)), NU splits per round trip.
-template <int NS, int NU, typename SegK>
+// This code runs once per layer from a cold instruction cache: compile-time head_dim / group (no integer divisions), one
+// max + NU exponentials per segment and round instead of an online rescale per split.
+template <int HD, int GROUP, int NS, int NU, typename SegK>
 __device__ __forceinline__ void mega_merge_segments(int q0, int nseg, SegK seg_k, int lane, int nsplit, uint32_t want, uint32_t xfrag) {
     const MegaArgs& a = c_mega;
-    const int group = a.nh / a.nkv;
-    const int head_lane0 = a.hd >= 64 ? 0 : (lane & 16);   // a segment spans one head (two when head_dim is 32)
+    const int head_lane0 = HD >= 64 ? 0 : (lane & 16);   // a segment spans one head (two when head_dim is 32)
     float Mx[NS], L[NS], acc0[NS], acc1[NS];
     int kk[NS];
+    const unsigned long long* pacc[NS];
+    const unsigned long long* pml[NS];
 #pragma unroll
-    for (int j = 0; j < NS; j++) { Mx[j] = -INFINITY; L[j] = 0.f; acc0[j] = 0.f; acc1[j] = 0.f; kk[j] = seg_k(min(q0 + j, nseg - 1)) + 2 * lane; }
+    for (int j = 0; j < NS; j++) {
+        Mx[j] = -INFINITY; L[j] = 0.f; acc0[j] = 0.f; acc1[j] = 0.f;
+        kk[j] = seg_k(min(q0 + j, nseg - 1)) + 2 * lane;
+        const int head = kk[j] / HD, d = kk[j] % HD;
+        const size_t rbase = (static_cast<size_t>(head / GROUP) * a.nsplit_max) * GROUP + head % GROUP;   // record of split 0
+        pacc[j] = a.ll_pacc + rbase * HD + d;     // + split * GROUP * HD
+        pml[j] = a.ll_pml + rbase * 2;            // + split * GROUP * 2
+    }
     for (int s0 = 0; s0 < nsplit; s0 += NU) {
         uint4 wa[NS][NU], wm[NS];
+        const int my_sp = min(s0 + (lane & (NU - 1)), nsplit - 1);
         unsigned spins = 0;
         for (;;) {
 #pragma unroll
             for (int j = 0; j < NS; j++) {
-                const int head = kk[j] / a.hd, d = kk[j] % a.hd;
-                const size_t rbase = (static_cast<size_t>(head / group) * a.nsplit_max) * group + head % group;
 #pragma unroll
-                for (int u = 0; u < NU; u++) {
-                    const int sp = min(s0 + u, nsplit - 1);                 // clamped duplicates are masked below
-                    wa[j][u] = ll_ld2(a.ll_pacc + (rbase + static_cast<size_t>(sp) * group) * a.hd + d);
-                }
+                for (int u = 0; u < NU; u++) wa[j][u] = ll_ld2(pacc[j] + static_cast<size_t>(min(s0 + u, nsplit - 1)) * (GROUP * HD));   // clamped duplicates are masked below
                 // (max, sum) of split s0 + u: fetched by lane u of the head's lanes, handed round with shuffles
-                wm[j] = ll_ld2(a.ll_pml + (rbase + static_cast<size_t>(min(s0 + (lane & (NU - 1)), nsplit - 1)) * group) * 2);
+                wm[j] = ll_ld2(pml[j] + static_cast<size_t>(my_sp) * (GROUP * 2));
             }
             bool ok = true;
 #pragma unroll
@@ -414,24 +422,32 @@ __device__ __forceinline__ void mega_merge_segments(int q0, int nseg, SegK seg_k
         }
 #pragma unroll
         for (int j = 0; j < NS; j++) {
+            float mu[NU], lu[NU];
+            float mn = Mx[j];
 #pragma unroll
             for (int u = 0; u < NU; u++) {
-                const float mu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].x), head_lane0 + u);
-                const float lu = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].z), head_lane0 + u);
-                if (s0 + u >= nsplit || mu == -INFINITY) continue;
-                const float mn = fmaxf(Mx[j], mu);
-                const float c_old = __expf(Mx[j] - mn), c_new = __expf(mu - mn);  // exp(-inf) = 0 on the first split
-                L[j] = L[j] * c_old + lu * c_new;
-                acc0[j] = acc0[j] * c_old + __uint_as_float(wa[j][u].x) * c_new;
-                acc1[j] = acc1[j] * c_old + __uint_as_float(wa[j][u].z) * c_new;
-                Mx[j] = mn;
+                mu[u] = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].x), head_lane0 + u);
+                lu[u] = __shfl_sync(0xffffffffu, __uint_as_float(wm[j].z), head_lane0 + u);
+                if (s0 + u >= nsplit) mu[u] = -INFINITY;   // clamped duplicate
+                mn = fmaxf(mn, mu[u]);
             }
+            if (mn == -INFINITY) continue;                  // nothing but empty splits so far
+            const float c_old = __expf(Mx[j] - mn);          // exp(-inf) = 0 in the first round
+            float l = L[j] * c_old, x0 = acc0[j] * c_old, x1 = acc1[j] * c_old;
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const float e = __expf(mu[u] - mn);          // 0 for empty splits (mu = -inf)
+                l = fmaf(lu[u], e, l);
+                x0 = fmaf(__uint_as_float(wa[j][u].x), e, x0);
+                x1 = fmaf(__uint_as_float(wa[j][u].z), e, x1);
+            }
+            L[j] = l; acc0[j] = x0; acc1[j] = x1; Mx[j] = mn;
         }
     }
 #pragma unroll
     for (int j = 0; j < NS; j++) {
         if (q0 + j < nseg) {
-            const float inv = 1.0f / L[j];
+            const float inv = __frcp_rn(L[j]);
             mega_put_frag(mega_frag_addr(xfrag, kk[j]), acc0[j] * inv, acc1[j] * inv);
         }
     }
@@ -443,6 +459,7 @@ __device__ __forceinline__ void mega_merge_segments(int q0, int nseg, SegK seg_k
 // group (four consecutive stages are in work at once, like four independent streams), and inside a window each warp of the
 // pair multiplies one half (KS/2 elements = T k16-steps). A warp polls, converts and keeps exactly the input elements it
 // multiplies; one wait and one arrive per warp per 8 KB of weights.
+template <int HD, int GROUP>
 __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaSmem& sm, ConsumerState& st_ref, int pi, int pos, int tid) {
     const MegaArgs& a = c_mega;
     ConsumerState& st = st_ref;
@@ -511,9 +528,9 @@ __device__ __forceinline__ void mega_gemv_phase(const PhaseRegs& ph, const MegaS
         const int nsplit = mega_attn_plan(a.nsplit_max, pos + 1, a.attn_tps, a.nh, gridDim.x).nsplit;
         for (int q0 = 0; q0 < nseg;) {
             const int n = nseg - q0;
-            if (n >= 3) { mega_merge_segments<4, 4>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 4; }
-            else if (n == 2) { mega_merge_segments<2, 8>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 2; }
-            else { mega_merge_segments<1, 16>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 1; }
+            if (n >= 3) { mega_merge_segments<HD, GROUP, 4, 4>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 4; }
+            else if (n == 2) { mega_merge_segments<HD, GROUP, 2, 8>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 2; }
+            else { mega_merge_segments<HD, GROUP, 1, 16>(q0, nseg, seg_k, lane, nsplit, want, sm.xfrag); q0 += 1; }
         }
     } else {
         const unsigned long long* src = type == PH_DOWN ? a.ll_act : a.ll_h;
@@ -787,7 +804,7 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int j = jb + (u * kMegaConsumerWarps + w) * TPW + sub;
-            page[u] = j < j1 ? ld_nc_early_s32(a.block_table + j / a.page_size) : 0;
+            page[u] = j < j1 ? ld_nc_early_s32(a.block_table + (j >> a.page_shift)) : 0;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -795,7 +812,7 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
             kw[u] = make_uint4(0, 0, 0, 0);
             vw[u] = make_uint4(0, 0, 0, 0);
             if (j < j1 && j != pos) {
-                const int off = j % a.page_size;
+                const int off = j & (a.page_size - 1);
                 kw[u] = ld_cg_early(kv.at(page[u], 0, off) + kvh * HD + sl * 8);
                 vw[u] = ld_cg_early(kv.at(page[u], 1, off) + kvh * HD + sl * 8);
             }
@@ -852,7 +869,7 @@ __device__ __forceinline__ void mega_attn_item_body(uint16_t* kv_pool, uint32_t 
                 vw[u] = make_uint4(pack_bf16x2(v_new[0], v_new[1]), pack_bf16x2(v_new[2], v_new[3]), pack_bf16x2(v_new[4], v_new[5]), pack_bf16x2(v_new[6], v_new[7]));
                 if (g0 == 0) {  // one writer per kv head. No fence here: the line is first read by the NEXT token, and this
                                 // CTA fences once per token before it publishes its argmax key (readers fence after the keys)
-                    const int page = __ldg(a.block_table + j / a.page_size), off = j % a.page_size;
+                    const int page = __ldg(a.block_table + (j >> a.page_shift)), off = j & (a.page_size - 1);
                     *reinterpret_cast<uint4*>(kv.at(page, 0, off) + kvh * HD + sl * 8) = kw[u];
                     *reinterpret_cast<uint4*>(kv.at(page, 1, off) + kvh * HD + sl * 8) = vw[u];
                 }
@@ -1193,7 +1210,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) mega_decode_kernel() {
                 if (a.prof && step == a.n_steps - 1 && tid == 0 && blockIdx.x < 160)
                     a.prof[(16 + 160 + blockIdx.x) * pstride + pi] = item < n_items ? globaltimer_ns() : 0ull;
             } else {
-                mega_gemv_phase(ph, sm, st, pi, pos, tid);
+                mega_gemv_phase<HD, GROUP>(ph, sm, st, pi, pos, tid);
             }
             if (ph.type == PH_LMHEAD) {
                 // CTA-level argmax, then one key per CTA
