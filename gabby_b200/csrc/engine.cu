@@ -1025,6 +1025,17 @@ CUtensorMap make_kmajor_map(const uint16_t* ptr, int64_t rows, int64_t cols, int
 void gemm_bf16(b2l_ctx* c, const uint16_t* A, const uint16_t* W, GemmArgs g) {
     B2L_CHECK(g.K % kGemmBK == 0 && g.K >= kGemmBK, "gemm: K must be a multiple of 64");
     B2L_CHECK(g.N % 128 == 0, "gemm: N must be a multiple of 128");
+    static const bool persistent_ok = [] { const char* e = std::getenv("B2L_GEMM_PERSISTENT"); return !e || std::atoi(e) != 0; }();   // development switch
+    if (persistent_ok && g.N % kGemmPBN == 0) {
+        // persistent 128 x 256 tiles, one CTA per SM (gemm_bf16_persistent_kernel)
+        const CUtensorMap ma = make_kmajor_map(A, g.M, g.K, kGemmBM), mw = make_kmajor_map(W, g.N, g.K, kGemmPBN);
+        ensure_smem_optin(reinterpret_cast<const void*>(gemm_bf16_persistent_kernel), c->p.device, kGemmPSmem);
+        const int total = ((g.M + kGemmBM - 1) / kGemmBM) * (g.N / kGemmPBN);
+        gemm_bf16_persistent_kernel<<<std::min(total, c->prop.multiProcessorCount), kGemmThreads, kGemmPSmem, c->stream>>>(ma, mw, g);
+        B2L_CUDA(cudaGetLastError());
+        c->launched++;
+        return;
+    }
     constexpr int BN = 128;
     const CUtensorMap ma = make_kmajor_map(A, g.M, g.K, kGemmBM), mw = make_kmajor_map(W, g.N, g.K, BN);
     const size_t smem = static_cast<size_t>(kGemmStages) * (kGemmBM * kGemmBK * 2 + BN * kGemmBK * 2) + 16 * kGemmStages + 64 + 1024;

@@ -196,4 +196,177 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
 }
 
+
+// ---- persistent version: 128 x 256 tiles, double-buffered TMEM accumulator ------------------------------------------------
+// One CTA per SM walks a static tile schedule. The 128 x 128 kernel above reads (128 + 128) x 16 x 2 B = 8 KB of shared memory
+// per 64-clock MMA -- exactly the 128 B/clk the SM's shared memory delivers, so the tensor pipe can never be kept full. A
+// 128 x 256 tile reads 12 KB per 128-clock MMA (96 B/clk). The whole TMEM (512 columns) holds TWO fp32 accumulators: the
+// epilogue warps drain tile i (tcgen05.ld -> fused epilogue -> global) while the MMA thread already fills tile i + 1, and the
+// TMA ring (4 stages x 48 KB) runs across tile boundaries, so neither the pipeline fill nor the epilogue is exposed.
+// Tile order: bands of kGemmBandN column tiles, row tiles fastest inside a band (the 148 tiles in flight then share ~18 A row
+// tiles and the band's 8 W column tiles: everything but the first touch comes out of L2).
+constexpr int kGemmPBN = 256, kGemmPStages = 4, kGemmBandN = 8;
+constexpr uint32_t kGemmPStageA = kGemmBM * kGemmBK * 2, kGemmPStageB = kGemmPBN * kGemmBK * 2;
+constexpr size_t kGemmPSmem = static_cast<size_t>(kGemmPStages) * (kGemmPStageA + kGemmPStageB) + 256 + 1024;
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// tile t of the schedule -> (row tile, column tile)
+__device__ __forceinline__ void gemm_tile_coords(int t, int m_tiles, int n_tiles, int& mt, int& nt) {
+    const int band_tiles = kGemmBandN * m_tiles;
+    const int band = t / band_tiles, r = t - band * band_tiles;
+    const int bw = min(kGemmBandN, n_tiles - band * kGemmBandN);   // the last band may be narrower
+    mt = r / bw;
+    nt = band * kGemmBandN + (r - mt * bw);
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t gsm[];
+    const uint32_t base = (smem_u32(gsm) + 1023u) & ~1023u;
+    const uint32_t sA = base, sB = base + kGemmPStages * kGemmPStageA;
+    const uint32_t bars = sB + kGemmPStages * kGemmPStageB;
+    const uint32_t full = bars, empty = bars + 8 * kGemmPStages, tmem_full = bars + 16 * kGemmPStages, tmem_empty = tmem_full + 16,
+                   tmem_slot = tmem_empty + 16;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_kblocks = g.K / kGemmBK;
+    const int m_tiles = (g.M + kGemmBM - 1) / kGemmBM, n_tiles = g.N / kGemmPBN;
+    const int total = m_tiles * n_tiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < kGemmPStages; s++) {
+            mbar_init(full + 8 * s, 1);
+            mbar_init(empty + 8 * s, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(tmem_full + 8 * i, 1);
+            mbar_init(tmem_empty + 8 * i, 4);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the whole TMEM: two 256-column accumulators (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- TMA producer: the ring runs across tile boundaries ----
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                int mt, nt;
+                gemm_tile_coords(t, m_tiles, n_tiles, mt, nt);
+                for (int kb = 0; kb < n_kblocks; kb++, it++) {
+                    const uint32_t s = it % kGemmPStages, parity = (it / kGemmPStages) & 1;
+                    mbar_wait_spin(empty + 8 * s, parity ^ 1);
+                    mbar_arrive_expect_tx(full + 8 * s, kGemmPStageA + kGemmPStageB);
+                    tma_load_2d(sA + s * kGemmPStageA, &map_a, kb * kGemmBK, mt * kGemmBM, full + 8 * s);
+                    tma_load_2d(sB + s * kGemmPStageB, &map_w, kb * kGemmBK, nt * kGemmPBN, full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer ----
+            constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmPBN);
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
+                const uint32_t acc = ti & 1;
+                mbar_wait_spin(tmem_empty + 8 * acc, ((ti >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kGemmPBN;
+                for (int kb = 0; kb < n_kblocks; kb++, it++) {
+                    const uint32_t s = it % kGemmPStages, parity = (it / kGemmPStages) & 1;
+                    mbar_wait_spin(full + 8 * s, parity);
+                    tcgen05_fence_after();
+                    const uint64_t da = umma_smem_desc(sA + s * kGemmPStageA), db = umma_smem_desc(sB + s * kGemmPStageB);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 16; k++) umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    tcgen05_commit(empty + 8 * s);
+                }
+                tcgen05_commit(tmem_full + 8 * acc);
+            }
+        }
+    } else {
+        // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4, one output row per thread ----
+        const int quarter = warp & 3;
+        uint32_t ti = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
+            int mt, nt;
+            gemm_tile_coords(t, m_tiles, n_tiles, mt, nt);
+            const uint32_t acc = ti & 1;
+            const int row = mt * kGemmBM + quarter * 32 + lane;
+            const int n0 = nt * kGemmPBN;
+            mbar_wait_spin(tmem_full + 8 * acc, (ti >> 1) & 1);
+            tcgen05_fence_after();
+            const uint32_t t_row = tmem_base + acc * kGemmPBN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kGemmPBN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + c0, r);
+                if (row < g.M) {
+                    const int col = n0 + c0;
+                    if (g.epilogue == GEMM_STORE_F32) {
+                        float4* dst = reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row) * g.ldc + col);
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                    } else if (g.epilogue == GEMM_ADD_F32) {
+                        float4* dst = reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row) * g.ldc + col);
+                        float4 v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[i] = dst[i];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            v[i].x += __uint_as_float(r[4 * i]); v[i].y += __uint_as_float(r[4 * i + 1]);
+                            v[i].z += __uint_as_float(r[4 * i + 2]); v[i].w += __uint_as_float(r[4 * i + 3]);
+                            dst[i] = v[i];
+                        }
+                    } else if (g.epilogue == GEMM_STORE_BF16) {
+                        uint4* dst = reinterpret_cast<uint4*>(g.c_bf16 + static_cast<size_t>(row) * g.ldc + col);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            dst[i] = make_uint4(pack_bf16x2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
+                                                pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
+                                                pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
+                                                pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+                    } else {  // GEMM_SWIGLU_BF16: W rows are (gate, up) pairs -> 16 outputs per 32 columns
+                        uint32_t o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const float g0 = __uint_as_float(r[4 * i]), u0 = __uint_as_float(r[4 * i + 1]);
+                            const float g1 = __uint_as_float(r[4 * i + 2]), u1 = __uint_as_float(r[4 * i + 3]);
+                            o[i] = pack_bf16x2((g0 / (1.0f + __expf(-g0))) * u0, (g1 / (1.0f + __expf(-g1))) * u1);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(g.c_bf16 + static_cast<size_t>(row) * g.ldc + (col >> 1));
+                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // this warp's quarter of the accumulator may be overwritten
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 }  // namespace b2l

@@ -17,7 +17,10 @@ def _rand_bits(rng, shape, scale):
     return synth.f32_to_bf16_bits((rng.standard_normal(shape) * scale).astype(np.float32))
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (200, 384, 2048), (1, 128, 128), (384, 128, 8192)])
+# N % 256 == 0 runs the persistent 128 x 256-tile kernel: (2500, 2304, 256) is 180 tiles on 148 CTAs (second tile per CTA,
+# both TMEM accumulators, ring wrap across tiles, narrow last column band, ragged last row tile)
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 512), (200, 384, 2048), (1, 128, 128), (384, 128, 8192),
+                                   (2500, 2304, 256), (300, 512, 4096), (5000, 2048, 64), (1, 256, 64)])
 def test_gemm_fp32_store_matches_float64(M, N, K):
     from gabby_b200 import _capi
     rng = np.random.default_rng(M + N + K)
@@ -39,6 +42,24 @@ def test_gemm_epilogues():
     Ca, _ = _capi.op_gemm_bf16(A, W, epilogue=2, c_in=R)                # residual add
     assert np.abs(Ca - (R + ref)).max() < 1e-3 * max(1.0, np.abs(ref).max())
     Cs, _ = _capi.op_gemm_bf16(A, W, epilogue=3)                        # SwiGLU over (gate, up) row pairs of W
+    g, u = ref[:, 0::2], ref[:, 1::2]
+    sw = (g / (1.0 + np.exp(-g))) * u
+    assert Cs.shape == (M, N // 2)
+    assert np.abs(Cs - sw).max() < 2.0 ** -7 * np.abs(sw).max() + 1e-3
+
+
+def test_gemm_epilogues_persistent_many_tiles():
+    from gabby_b200 import _capi
+    rng = np.random.default_rng(11)
+    M, N, K = 2000, 2560, 192       # 16 x 10 tiles of 128 x 256 on 148 CTAs
+    A, W = _rand_bits(rng, (M, K), 1.0), _rand_bits(rng, (N, K), 1.0 / np.sqrt(K))
+    ref = _ref(A, W)
+    Cb, _ = _capi.op_gemm_bf16(A, W, epilogue=1)
+    assert np.abs(Cb - ref).max() < 2.0 ** -8 * np.abs(ref).max() + 1e-3
+    R = rng.standard_normal((M, N)).astype(np.float32)
+    Ca, _ = _capi.op_gemm_bf16(A, W, epilogue=2, c_in=R)
+    assert np.abs(Ca - (R + ref)).max() < 1e-3 * max(1.0, np.abs(ref).max())
+    Cs, _ = _capi.op_gemm_bf16(A, W, epilogue=3)
     g, u = ref[:, 0::2], ref[:, 1::2]
     sw = (g / (1.0 + np.exp(-g))) * u
     assert Cs.shape == (M, N // 2)
