@@ -30,6 +30,7 @@
 #undef MEGA_NS
 #include "gemm_tcgen05.cuh"
 #include "flash_prefill.cuh"
+#include "flash_prefill_tc.cuh"
 #include "skinny_gemm.cuh"
 #include "attn_decode_mma.cuh"
 #include "synth.cuh"
@@ -549,6 +550,7 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
 }
 
 void gemm_bf16(b2l_ctx* c, const uint16_t* A, const uint16_t* W, GemmArgs g);  // defined with the tensor-map helpers below
+CUtensorMap make_kmajor_map(const uint16_t* ptr, int64_t rows, int64_t cols, int box_rows);
 
 constexpr int kPfAttnChunk = 128;  // rows per split-K attention launch in the GEMM prefill path
 
@@ -572,6 +574,20 @@ void prefill_alloc(b2l_ctx* c) {
     c->pf_part_ml = dalloc<float>(c, row_splits * c->nkv_l * c->group * 2);
     c->pf_counters = dalloc<int>(c, rows * c->nkv_l);
     c->pf_tiles = dalloc<PrefillTile>(c, T / 1 + static_cast<size_t>(c->p.max_batch));  // <= one tile per row in the worst case
+    c->pf_tiles_tc = dalloc<PrefillTile>(c, T / 1 + static_cast<size_t>(c->p.max_batch));
+    {
+        // tcgen05 attention: one tensor map over every layer's pool, rows = [layer][page][K|V][slot] of kvd elements
+        const int ps = c->p.page_size;
+        const int64_t rows = static_cast<int64_t>(c->L) * c->p.num_pages * 2 * ps;
+        const char* tc_env = std::getenv("B2L_FLASH_TC");   // development / test switch, read per context: 0 = the mma.sync kernel
+        const bool tc_on = !tc_env || std::atoi(tc_env) != 0;
+        c->flash_tc_ok = tc_on && (c->hd == 64 || c->hd == 128) && ps >= 8 && ps <= 128 && 128 % ps == 0 && ps % 8 == 0 && rows < (1ll << 31);
+        if (c->flash_tc_ok) {
+            const CUtensorMap m = make_kmajor_map(c->kv_base, rows, c->kvd_l, ps);
+            static_assert(sizeof(CUtensorMap) <= sizeof(c->kv_map), "kv_map storage");
+            std::memcpy(c->kv_map, &m, sizeof(m));
+        }
+    }
     B2L_CUDA(cudaMemset(c->pf_counters, 0, sizeof(int) * rows * c->nkv_l));
 }
 
@@ -597,7 +613,23 @@ void prefill_gemm(b2l_ctx* c, int T, int n_seq, int tap_row0) {
         c->launched++;
         gemm_bf16(c, c->pf_xn, w.w_qkv, GemmArgs{c->pf_qkv, nullptr, T, c->qkv_l, c->H, c->qkv_l, GEMM_STORE_F32});
         launch(c, rope_kv_kernel, dim3(T), dim3(256), 0, c->pf_qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
-        if (c->hd == 64 || c->hd == 128) {
+        if (c->flash_tc_ok) {
+            // flash-style causal attention on tcgen05 / TMEM (flash_prefill_tc.cuh)
+            CUtensorMap mkv;
+            std::memcpy(&mkv, c->kv_map, sizeof(mkv));
+            const FlashTcArgs fa{c->pf_qkv, c->qkv_l, c->d_block_tables, c->max_blocks_cap, static_cast<const PrefillTile*>(c->pf_tiles_tc),
+                                 c->pf_attn16, c->qd_l, c->group, scale * 1.4426950408889634f, c->p.page_size,
+                                 static_cast<long long>(l) * c->p.num_pages * 2 * c->p.page_size};
+            const dim3 grid(c->pf_n_tiles_tc, c->nh_l);
+            auto go = [&](auto kern, size_t smem) {
+                ensure_smem_optin(reinterpret_cast<const void*>(kern), c->p.device, static_cast<int>(smem));
+                kern<<<grid, kFtcThreads, smem, c->stream>>>(mkv, fa);
+            };
+            if (c->hd == 64) go(flash_prefill_tc_kernel<64>, FtcSmem<64>::total);
+            else go(flash_prefill_tc_kernel<128>, FtcSmem<128>::total);
+            B2L_CUDA(cudaGetLastError());
+            c->launched++;
+        } else if (c->hd == 64 || c->hd == 128) {
             // flash-style causal attention over the paged cache, tensor-core S and PV, bf16 output
             FlashArgs fa{c->pf_qkv, c->qkv_l, kv, c->d_block_tables, c->max_blocks_cap, static_cast<const PrefillTile*>(c->pf_tiles),
                          c->pf_attn16, c->qd_l, c->group, scale * 1.4426950408889634f};
@@ -1031,7 +1063,7 @@ void gemm_bf16(b2l_ctx* c, const uint16_t* A, const uint16_t* W, GemmArgs g) {
         const CUtensorMap ma = make_kmajor_map(A, g.M, g.K, kGemmBM), mw = make_kmajor_map(W, g.N, g.K, kGemmPBN);
         ensure_smem_optin(reinterpret_cast<const void*>(gemm_bf16_persistent_kernel), c->p.device, kGemmPSmem);
         const int total = ((g.M + kGemmBM - 1) / kGemmBM) * (g.N / kGemmPBN);
-        gemm_bf16_persistent_kernel<<<std::min(total, c->prop.multiProcessorCount), kGemmThreads, kGemmPSmem, c->stream>>>(ma, mw, g);
+        gemm_bf16_persistent_kernel<<<std::min(total, c->prop.multiProcessorCount), kGemmPThreads, kGemmPSmem, c->stream>>>(ma, mw, g);
         B2L_CUDA(cudaGetLastError());
         c->launched++;
         return;
@@ -1465,6 +1497,16 @@ int b2l_prefill(b2l_ctx* c, int n_seq, const int32_t* tokens, const int32_t* q_l
             }
             c->pf_n_tiles = static_cast<int>(tiles.size());
             B2L_CUDA(cudaMemcpyAsync(c->pf_tiles, tiles.data(), sizeof(PrefillTile) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
+            std::vector<PrefillTile> tiles_tc;   // 256 consecutive positions per CTA of the tcgen05 attention, longest contexts first
+            row = 0;
+            for (int i = 0; i < n_seq; i++) {
+                for (int j = 0; j < q_lens[i]; j += 2 * kFtcBQ)
+                    tiles_tc.push_back(PrefillTile{static_cast<int>(row + j), std::min(2 * kFtcBQ, q_lens[i] - j), ctx_lens[i] + j, i});
+                row += q_lens[i];
+            }
+            std::stable_sort(tiles_tc.begin(), tiles_tc.end(), [](const PrefillTile& x, const PrefillTile& y) { return x.pos0 + x.n_rows > y.pos0 + y.n_rows; });
+            c->pf_n_tiles_tc = static_cast<int>(tiles_tc.size());
+            B2L_CUDA(cudaMemcpyAsync(c->pf_tiles_tc, tiles_tc.data(), sizeof(PrefillTile) * tiles_tc.size(), cudaMemcpyHostToDevice, c->stream));
             B2L_CUDA(cudaStreamSynchronize(c->stream));   // pos/slot/last are stack vectors
             prefill_gemm(c, static_cast<int>(total), n_seq, c->taps ? 0 : -1);
         }

@@ -119,6 +119,10 @@ struct b2l_ctx {
     int* pf_counters = nullptr;
     void* pf_tiles = nullptr;        // device PrefillTile[] (flash prefill attention work list)
     int pf_n_tiles = 0;
+    void* pf_tiles_tc = nullptr;     // device PrefillTile[] of up to 256 rows, heaviest first (flash_prefill_tc.cuh)
+    int pf_n_tiles_tc = 0;
+    bool flash_tc_ok = false;        // head_dim / page size fit the tcgen05 attention kernel
+    alignas(64) unsigned char kv_map[128] = {};   // CUtensorMap over the whole KV pool (rows of kvd elements, box = one page x 64 dims)
 
     // batched decode on the tensor cores (skinny_gemm.cuh)
     bool skinny_ok = false;

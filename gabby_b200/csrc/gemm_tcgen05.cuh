@@ -206,6 +206,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 // Tile order: bands of kGemmBandN column tiles, row tiles fastest inside a band (the 148 tiles in flight then share ~18 A row
 // tiles and the band's 8 W column tiles: everything but the first touch comes out of L2).
 constexpr int kGemmPBN = 256, kGemmPStages = 4, kGemmBandN = 8;
+constexpr int kGemmPThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter: column halves of the tile)
 constexpr uint32_t kGemmPStageA = kGemmBM * kGemmBK * 2, kGemmPStageB = kGemmPBN * kGemmBK * 2;
 constexpr size_t kGemmPSmem = static_cast<size_t>(kGemmPStages) * (kGemmPStageA + kGemmPStageB) + 256 + 1024;
 
@@ -229,7 +230,13 @@ __device__ __forceinline__ void gemm_tile_coords(int t, int m_tiles, int n_tiles
     nt = band * kGemmBandN + (r - mt * bw);
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__device__ __forceinline__ float4 ldg_f4_early(const float4* p) {   // issued where it is written (ahead of the TMEM wait it overlaps)
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kGemmPThreads, 1)
 gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
     extern __shared__ __align__(1024) uint8_t gsm[];
     const uint32_t base = (smem_u32(gsm) + 1023u) & ~1023u;
@@ -250,7 +257,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(tmem_full + 8 * i, 1);
-            mbar_init(tmem_empty + 8 * i, 4);   // one arrival per epilogue warp
+            mbar_init(tmem_empty + 8 * i, 8);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -301,40 +308,57 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
             }
         }
     } else {
-        // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4, one output row per thread ----
-        const int quarter = warp & 3;
+        // ---- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; one output row per thread ----
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        constexpr int kHalfCols = kGemmPBN / 2;
+        const bool add = g.epilogue == GEMM_ADD_F32;
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
             int mt, nt;
             gemm_tile_coords(t, m_tiles, n_tiles, mt, nt);
             const uint32_t acc = ti & 1;
             const int row = mt * kGemmBM + quarter * 32 + lane;
-            const int n0 = nt * kGemmPBN;
+            const bool live = row < g.M;
+            const int n0 = nt * kGemmPBN + half * kHalfCols;
+            // residual add: the old values do not depend on the accumulator -- fetch the first chunk before waiting for the
+            // MMAs and chunk c + 1 while chunk c is added and stored (scattered 16-byte reads: latency, not bandwidth)
+            float4 v[8];
+            const float4* src = reinterpret_cast<const float4*>(g.c_f32 + static_cast<size_t>(live ? row : 0) * g.ldc + n0);
+            if (add) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = ldg_f4_early(src + i);
+            }
             mbar_wait_spin(tmem_full + 8 * acc, (ti >> 1) & 1);
             tcgen05_fence_after();
-            const uint32_t t_row = tmem_base + acc * kGemmPBN + (static_cast<uint32_t>(quarter * 32) << 16);
+            const uint32_t t_row = tmem_base + acc * kGemmPBN + half * kHalfCols + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kGemmPBN; c0 += 32) {
+            for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(t_row + c0, r);
-                if (row < g.M) {
-                    const int col = n0 + c0;
-                    if (g.epilogue == GEMM_STORE_F32) {
-                        float4* dst = reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row) * g.ldc + col);
+                const int col = n0 + c0;
+                if (add) {
+                    float4 vn[8];
+                    if (c0 + 32 < kHalfCols) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                    } else if (g.epilogue == GEMM_ADD_F32) {
+                        for (int i = 0; i < 8; i++) vn[i] = ldg_f4_early(src + (c0 + 32) / 4 + i);
+                    }
+                    if (live) {
                         float4* dst = reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row) * g.ldc + col);
-                        float4 v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++) v[i] = dst[i];
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
                             v[i].x += __uint_as_float(r[4 * i]); v[i].y += __uint_as_float(r[4 * i + 1]);
                             v[i].z += __uint_as_float(r[4 * i + 2]); v[i].w += __uint_as_float(r[4 * i + 3]);
                             dst[i] = v[i];
                         }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = vn[i];
+                } else if (live) {
+                    if (g.epilogue == GEMM_STORE_F32) {
+                        float4* dst = reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row) * g.ldc + col);
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
                     } else if (g.epilogue == GEMM_STORE_BF16) {
                         uint4* dst = reinterpret_cast<uint4*>(g.c_bf16 + static_cast<size_t>(row) * g.ldc + col);
 #pragma unroll
@@ -359,7 +383,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // this warp's quarter of the accumulator may be overwritten
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // this warp's part of the accumulator may be overwritten
         }
     }
     __syncthreads();

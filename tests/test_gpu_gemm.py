@@ -133,3 +133,64 @@ def test_gemm_prefill_continues_cached_context_like_the_exact_path():
         outs.append((int(nxt[0]), eng.logits(0, 1)[0].copy()))
     assert outs[0][0] == outs[1][0]
     assert np.abs(outs[0][1] - outs[1][1]).max() < 5e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 / TMEM flash prefill attention (flash_prefill_tc.cuh)
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("preset,layers,lens", [
+    ("tiny128", None, [400, 140, 5, 257]),     # head_dim 128: both query tiles of a CTA, 1-4 kv tiles, ragged tails, a 1-row second tile
+    ("1b", 2, [300, 129]),                     # head_dim 64, GQA group 4
+    ("3b", 2, [260]),                          # head_dim 128, GQA group 3
+])
+def test_flash_tc_matches_mma_sync_kernel_and_oracle(preset, layers, lens, monkeypatch):
+    """Same prompts through the prefill pipeline with the tcgen05 attention kernel and with the mma.sync kernel (B2L_FLASH_TC=0):
+    every row of the last layer's residual stream must agree (both round q, K, V and P to bf16 at the same points; the
+    running-max schedules differ: 64- vs 128-token tiles), and the tcgen05 run must match the oracle like the old kernel does."""
+    from oracle import pyoracle as po
+    from tests.helpers import synth_tensors, make_engine, contiguous_tables, cosine
+    arch, tensors = synth_tensors(preset, layers, 21)
+    prompts = [synth.synth_prompt(n, arch.vocab_size, arch.bos_token_id, 900 + i) for i, n in enumerate(lens)]
+    L = arch.num_hidden_layers
+    outs = []
+    for tc in ("1", "0"):
+        monkeypatch.setenv("B2L_FLASH_TC", tc)
+        eng = make_engine(arch, tensors, max_batch=len(lens), max_positions=512, max_prefill_tokens=sum(lens) + 8, num_pages=len(lens) * 32)
+        eng.set_prefill_mode(1)
+        eng.set_taps(True)
+        bt = contiguous_tables(len(lens), eng.max_blocks)
+        first = eng.prefill(prompts, [0] * len(lens), bt)
+        outs.append((first.copy(), eng.logits(0, len(lens)).copy(), eng.hidden(L, 0, sum(lens)).copy()))
+        eng.close()
+    (f1, lg1, h1), (f0, lg0, h0) = outs
+    scale = np.abs(h0).max()
+    assert np.abs(h1 - h0).max() < 2e-2 * max(1.0, scale) and cosine(h1, h0) > 0.99999, float(np.abs(h1 - h0).max())
+    assert np.abs(lg1 - lg0).max() < 6e-2   # bf16 activations: a value on a rounding boundary may flip (same bound as against the oracle)
+    om = po.OracleModel(arch, tensors, 512)
+    row = 0
+    for i, p in enumerate(prompts):
+        s = om.seq(po.ORC_KV_BF16 | po.ORC_ACT_BF16 | po.ORC_QP_BF16)
+        ol, oh = s.forward(p, want_hidden=True)
+        assert np.abs(lg1[i] - ol[0]).max() < 6e-2 and cosine(lg1[i], ol[0]) > 0.9999, (i, float(np.abs(lg1[i] - ol[0]).max()))
+        hd = np.abs(h1[row:row + len(p)] - oh[L])
+        assert hd.max() < 8e-2 and hd.mean() < 1e-2, (i, float(hd.max()))
+        row += len(p)
+
+
+def test_flash_tc_continues_cached_context():
+    """Second prefill call appends to 70 cached tokens: query positions start mid-page and mid-tile."""
+    from tests.helpers import synth_tensors, make_engine, contiguous_tables
+    arch, tensors = synth_tensors("tiny128", None, 77)
+    prompt = synth.synth_prompt(330, arch.vocab_size, arch.bos_token_id, 9)
+    outs = []
+    for mode in (0, 1):
+        eng = make_engine(arch, tensors, max_positions=512, max_prefill_tokens=512, num_pages=40)
+        eng.set_prefill_mode(mode)
+        bt = contiguous_tables(1, eng.max_blocks)
+        eng.prefill([prompt[:70]], [0], bt)
+        nxt = eng.prefill([prompt[70:]], [70], bt)
+        outs.append((int(nxt[0]), eng.logits(0, 1)[0].copy()))
+        eng.close()
+    assert outs[0][0] == outs[1][0]
+    assert np.abs(outs[0][1] - outs[1][1]).max() < 5e-2
