@@ -133,15 +133,31 @@ __global__ void __launch_bounds__(kFtcThreads, 1) flash_prefill_tc_kernel(const 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // ---- Q: fp32 (rotated) -> bf16, K-major panels with the 128-byte swizzle the MMA descriptors expect ----
-    for (int i = tid; i < 2 * kFtcBQ * (HD / 8); i += kFtcThreads) {
-        const int r = i / (HD / 8), c8 = i % (HD / 8);            // row 0..255, 16-byte piece (8 dims)
-        const int row = tile.row0 + min(r, tile.n_rows - 1);      // rows past the tile repeat the last row
-        const float4* src = reinterpret_cast<const float4*>(a.qkv + static_cast<size_t>(row) * a.ld + head * HD + c8 * 8);
-        const float4 x = src[0], y = src[1];
-        const uint32_t t = r >> 7, rr = r & 127, panel = c8 >> 3, piece = c8 & 7;
-        const uint32_t dst = sQ + t * kTileBytes + panel * kPanelBytes + rr * 128 + ((piece ^ (rr & 7)) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(x.x, x.y)), "r"(pack_bf16x2(x.z, x.w)),
-                     "r"(pack_bf16x2(y.x, y.y)), "r"(pack_bf16x2(y.z, y.w)) : "memory");
+    // (the loads of a batch are all in flight together: one load per round trip made this prologue a fifth of the kernel's time)
+    constexpr int kQPieces = 2 * kFtcBQ * (HD / 8), kQBatch = 7;
+#pragma unroll 1
+    for (int i0 = tid; i0 < kQPieces; i0 += kQBatch * kFtcThreads) {
+        float4 x[kQBatch], y[kQBatch];
+#pragma unroll
+        for (int b = 0; b < kQBatch; b++) {
+            const int i = min(i0 + b * kFtcThreads, kQPieces - 1);
+            const int r = i / (HD / 8), c8 = i % (HD / 8);            // row 0..255, 16-byte piece (8 dims)
+            const int row = tile.row0 + min(r, tile.n_rows - 1);      // rows past the tile repeat the last row
+            const float4* src = reinterpret_cast<const float4*>(a.qkv + static_cast<size_t>(row) * a.ld + head * HD + c8 * 8);
+            x[b] = ldg_f4_early(src);
+            y[b] = ldg_f4_early(src + 1);
+        }
+#pragma unroll
+        for (int b = 0; b < kQBatch; b++) {
+            const int i = i0 + b * kFtcThreads;
+            if (i < kQPieces) {
+                const uint32_t r = i / (HD / 8), c8 = i % (HD / 8);
+                const uint32_t t = r >> 7, rr = r & 127, panel = c8 >> 3, piece = c8 & 7;
+                const uint32_t dst = sQ + t * kTileBytes + panel * kPanelBytes + rr * 128 + ((piece ^ (rr & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(x[b].x, x[b].y)), "r"(pack_bf16x2(x[b].z, x[b].w)),
+                             "r"(pack_bf16x2(y[b].x, y[b].y)), "r"(pack_bf16x2(y[b].z, y[b].w)) : "memory");
+            }
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core's async reads
     tcgen05_fence_before();

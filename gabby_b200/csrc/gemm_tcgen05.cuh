@@ -206,9 +206,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 // Tile order: bands of kGemmBandN column tiles, row tiles fastest inside a band (the 148 tiles in flight then share ~18 A row
 // tiles and the band's 8 W column tiles: everything but the first touch comes out of L2).
 constexpr int kGemmPBN = 256, kGemmPStages = 4, kGemmBandN = 8;
-constexpr int kGemmPThreads = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter: column halves of the tile)
+constexpr int kGemmPThreads = 192;   // TMA warp, MMA warp, 4 epilogue warps (one per TMEM lane quarter)
+constexpr uint32_t kGemmPStgRow = 144, kGemmPStgWarp = 32 * kGemmPStgRow;   // per-warp transposition block: 32 rows x (32 fp32 + 16 B pad)
 constexpr uint32_t kGemmPStageA = kGemmBM * kGemmBK * 2, kGemmPStageB = kGemmPBN * kGemmBK * 2;
-constexpr size_t kGemmPSmem = static_cast<size_t>(kGemmPStages) * (kGemmPStageA + kGemmPStageB) + 256 + 1024;
+constexpr size_t kGemmPSmem = static_cast<size_t>(kGemmPStages) * (kGemmPStageA + kGemmPStageB) + 256 + 4 * kGemmPStgWarp + 1024;
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -243,7 +244,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
     const uint32_t sA = base, sB = base + kGemmPStages * kGemmPStageA;
     const uint32_t bars = sB + kGemmPStages * kGemmPStageB;
     const uint32_t full = bars, empty = bars + 8 * kGemmPStages, tmem_full = bars + 16 * kGemmPStages, tmem_empty = tmem_full + 16,
-                   tmem_slot = tmem_empty + 16;
+                   tmem_slot = tmem_empty + 16, stg_base = bars + 256;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_kblocks = g.K / kGemmBK;
@@ -257,7 +258,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(tmem_full + 8 * i, 1);
-            mbar_init(tmem_empty + 8 * i, 8);   // one arrival per epilogue warp
+            mbar_init(tmem_empty + 8 * i, 4);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -308,58 +309,64 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
             }
         }
     } else {
-        // ---- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; one output row per thread ----
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
-        constexpr int kHalfCols = kGemmPBN / 2;
-        const bool add = g.epilogue == GEMM_ADD_F32;
+        // ---- epilogue warps 2..5: TMEM lane quarter = warp % 4. tcgen05.ld hands every thread one output ROW; written like
+        // that, a warp's 16-byte accesses land in 32 different rows (the fp32 epilogues ran at a third of the main loop's pace
+        // and throttled it: ncu, o-projection shape, tensor pipe 60 % busy against 89 % with the bf16 SwiGLU epilogue). The
+        // fp32 epilogues therefore transpose each 32 x 32 block through shared memory: a warp instruction then covers four
+        // full 128-byte lines. ----
+        const int quarter = warp & 3;
+        const bool f32 = g.epilogue == GEMM_STORE_F32 || g.epilogue == GEMM_ADD_F32, add = g.epilogue == GEMM_ADD_F32;
+        const uint32_t stg = stg_base + static_cast<uint32_t>(warp - 2) * kGemmPStgWarp;
+        const int tr = lane >> 3, tc = (lane & 7) * 4;   // transposed mapping: lane -> row tr + 4 i, columns tc .. tc + 3
         uint32_t ti = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ti++) {
             int mt, nt;
             gemm_tile_coords(t, m_tiles, n_tiles, mt, nt);
             const uint32_t acc = ti & 1;
-            const int row = mt * kGemmBM + quarter * 32 + lane;
-            const bool live = row < g.M;
-            const int n0 = nt * kGemmPBN + half * kHalfCols;
-            // residual add: the old values do not depend on the accumulator -- fetch the first chunk before waiting for the
-            // MMAs and chunk c + 1 while chunk c is added and stored (scattered 16-byte reads: latency, not bandwidth)
+            const int row0 = mt * kGemmBM + quarter * 32;   // first row of this warp's 32
+            const int row = row0 + lane;
+            const int n0 = nt * kGemmPBN;
+            // residual add: the old values do not depend on the accumulator -- fetch the first block before waiting for the
+            // MMAs and block c + 1 while block c is added and stored
             float4 v[8];
-            const float4* src = reinterpret_cast<const float4*>(g.c_f32 + static_cast<size_t>(live ? row : 0) * g.ldc + n0);
             if (add) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = ldg_f4_early(src + i);
+                for (int i = 0; i < 8; i++)
+                    v[i] = ldg_f4_early(reinterpret_cast<const float4*>(g.c_f32 + static_cast<size_t>(min(row0 + tr + 4 * i, g.M - 1)) * g.ldc + n0 + tc));
             }
             mbar_wait_spin(tmem_full + 8 * acc, (ti >> 1) & 1);
             tcgen05_fence_after();
-            const uint32_t t_row = tmem_base + acc * kGemmPBN + half * kHalfCols + (static_cast<uint32_t>(quarter * 32) << 16);
+            const uint32_t t_row = tmem_base + acc * kGemmPBN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kHalfCols; c0 += 32) {
+            for (int c0 = 0; c0 < kGemmPBN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(t_row + c0, r);
                 const int col = n0 + c0;
-                if (add) {
+                if (f32) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        sts128f(stg + lane * kGemmPStgRow + i * 16, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                                 __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+                    __syncwarp();
                     float4 vn[8];
-                    if (c0 + 32 < kHalfCols) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) vn[i] = ldg_f4_early(src + (c0 + 32) / 4 + i);
-                    }
-                    if (live) {
-                        float4* dst = reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row) * g.ldc + col);
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            v[i].x += __uint_as_float(r[4 * i]); v[i].y += __uint_as_float(r[4 * i + 1]);
-                            v[i].z += __uint_as_float(r[4 * i + 2]); v[i].w += __uint_as_float(r[4 * i + 3]);
-                            dst[i] = v[i];
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++) v[i] = vn[i];
-                } else if (live) {
-                    if (g.epilogue == GEMM_STORE_F32) {
-                        float4* dst = reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row) * g.ldc + col);
+                    if (add && c0 + 32 < kGemmPBN) {
 #pragma unroll
                         for (int i = 0; i < 8; i++)
-                            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                    } else if (g.epilogue == GEMM_STORE_BF16) {
+                            vn[i] = ldg_f4_early(reinterpret_cast<const float4*>(g.c_f32 + static_cast<size_t>(min(row0 + tr + 4 * i, g.M - 1)) * g.ldc + col + 32 + tc));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        float4 x = lds128f(stg + (tr + 4 * i) * kGemmPStgRow + tc * 4);
+                        if (add) { x.x += v[i].x; x.y += v[i].y; x.z += v[i].z; x.w += v[i].w; }
+                        if (row0 + tr + 4 * i < g.M) *reinterpret_cast<float4*>(g.c_f32 + static_cast<size_t>(row0 + tr + 4 * i) * g.ldc + col + tc) = x;
+                    }
+                    __syncwarp();   // the block is rewritten by the next iteration
+                    if (add) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) v[i] = vn[i];
+                    }
+                } else if (row < g.M) {
+                    if (g.epilogue == GEMM_STORE_BF16) {
                         uint4* dst = reinterpret_cast<uint4*>(g.c_bf16 + static_cast<size_t>(row) * g.ldc + col);
 #pragma unroll
                         for (int i = 0; i < 4; i++)
@@ -383,7 +390,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // this warp's part of the accumulator may be overwritten
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * acc);   // this warp's quarter of the accumulator may be overwritten
         }
     }
     __syncthreads();
