@@ -220,8 +220,10 @@ struct RowMeta {
     int max_blocks;
 };
 
+// first_head = 0: rotate q in place and append k, v; first_head = nh: only the k heads and v (the tcgen05 prefill attention
+// rotates q itself while it stages it, flash_prefill_tc.cuh)
 __global__ void rope_kv_kernel(float* __restrict__ qkv, int ld, const float* __restrict__ rope, KvLayout kv,
-                               RowMeta rm, int nh, int nkv, int hd) {
+                               RowMeta rm, int nh, int nkv, int hd, int first_head) {
     pdl_launch_dependents();
     pdl_wait();
     const int r = blockIdx.x;
@@ -234,7 +236,7 @@ __global__ void rope_kv_kernel(float* __restrict__ qkv, int ld, const float* __r
     uint16_t* kdst = kv.at(page, 0, off);
     uint16_t* vdst = kv.at(page, 1, off);
     const int qd = nh * hd, kvd = nkv * hd;
-    for (int i = threadIdx.x; i < (nh + nkv) * half; i += blockDim.x) {
+    for (int i = first_head * half + threadIdx.x; i < (nh + nkv) * half; i += blockDim.x) {
         const int head = i / half, j = i % half;
         const float c = cs[2 * j], s = cs[2 * j + 1];
         float* v = row + head * hd;  // q heads then k heads are contiguous in the fused row

@@ -507,7 +507,7 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         const bool fuse_norm = sk && R <= 32 && c->p.tp_size == 1 && c->H <= 8192;
         if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R, nullptr, fuse_norm && l > 0);
         else gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
-        launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
+        launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd, 0);
         const bool fuse = sk && R <= 32;   // one row group: producers write the next projection's bf16 hi/lo operand directly
         const int skT = R <= 8 ? 8 : R <= 16 ? 16 : 32;
         AttnArgs aa{c->qkv, c->qkv_l, kv, rm, c->part_acc, c->part_ml, c->attn_counters, c->attn, c->qd_l, scale};
@@ -612,12 +612,12 @@ void prefill_gemm(b2l_ctx* c, int T, int n_seq, int tap_row0) {
         rmsnorm_bf16_kernel<<<T, 256, 0, c->stream>>>(c->pf_h, w.in_norm, c->pf_xn, c->H, eps);
         c->launched++;
         gemm_bf16(c, c->pf_xn, w.w_qkv, GemmArgs{c->pf_qkv, nullptr, T, c->qkv_l, c->H, c->qkv_l, GEMM_STORE_F32});
-        launch(c, rope_kv_kernel, dim3(T), dim3(256), 0, c->pf_qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd);
+        launch(c, rope_kv_kernel, dim3(T), dim3(256), 0, c->pf_qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd, c->flash_tc_ok ? c->nh_l : 0);
         if (c->flash_tc_ok) {
             // flash-style causal attention on tcgen05 / TMEM (flash_prefill_tc.cuh)
             CUtensorMap mkv;
             std::memcpy(&mkv, c->kv_map, sizeof(mkv));
-            const FlashTcArgs fa{c->pf_qkv, c->qkv_l, c->d_block_tables, c->max_blocks_cap, static_cast<const PrefillTile*>(c->pf_tiles_tc),
+            const FlashTcArgs fa{c->pf_qkv, c->qkv_l, c->rope, c->d_block_tables, c->max_blocks_cap, static_cast<const PrefillTile*>(c->pf_tiles_tc),
                                  c->pf_attn16, c->qd_l, c->group, scale * 1.4426950408889634f, c->p.page_size,
                                  static_cast<long long>(l) * c->p.num_pages * 2 * c->p.page_size};
             const dim3 grid(c->pf_n_tiles_tc, c->nh_l);

@@ -12,7 +12,7 @@
 //              tcgen05.ld S -> scale, causal mask, running max -> P = exp2(s - m) as bf16 written back over S
 //              (tcgen05.st), O rescaled in TMEM when the row maximum moved, at the end O / l -> bf16 -> global
 // TMEM: S0 | S1 (128 fp32 columns each; P aliases the first 64 columns of its S) | O0 | O1 (head_dim columns each).
-// q: fp32 [T][ld] already rotated (rope_kv_kernel), rounded to bf16 when staged; out: bf16 [T][ldo].
+// q: fp32 [T][ld] straight from the QKV GEMM: rotated (RoPE) and rounded to bf16 while it is staged; out: bf16 [T][ldo].
 // Math = oracle attention with ORC_KV_BF16 | ORC_QP_BF16 (same rounding points as flash_prefill.cuh).
 #pragma once
 #include <cuda.h>
@@ -24,8 +24,9 @@
 namespace b2l {
 
 struct FlashTcArgs {
-    const float* qkv;            // [T][ld] fp32, q heads first
+    const float* qkv;            // [T][ld] fp32, q heads first, NOT rotated
     int ld;
+    const float* rope;           // [max_positions][HD/2][2] (cos, sin)
     const int32_t* block_tables; // [n_slots][max_blocks]
     int max_blocks;
     const PrefillTile* tiles;    // up to 256 rows each
@@ -132,30 +133,50 @@ __global__ void __launch_bounds__(kFtcThreads, 1) flash_prefill_tc_kernel(const 
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ---- Q: fp32 (rotated) -> bf16, K-major panels with the 128-byte swizzle the MMA descriptors expect ----
-    // (the loads of a batch are all in flight together: one load per round trip made this prologue a fifth of the kernel's time)
-    constexpr int kQPieces = 2 * kFtcBQ * (HD / 8), kQBatch = 7;
+    // ---- Q: fp32 -> RoPE -> bf16, K-major panels with the 128-byte swizzle the MMA descriptors expect ----
+    // RoPE happens here (rope_kv_kernel's arithmetic): an item = 8 dims of the lower half of a row + their partners in the upper
+    // half. The loads of a batch are all in flight together (one load per round trip made this prologue a fifth of the
+    // kernel's time).
+    constexpr int kQItems = 2 * kFtcBQ * (HD / 16), kQBatch = 4;
 #pragma unroll 1
-    for (int i0 = tid; i0 < kQPieces; i0 += kQBatch * kFtcThreads) {
-        float4 x[kQBatch], y[kQBatch];
+    for (int i0 = tid; i0 < kQItems; i0 += kQBatch * kFtcThreads) {
+        float4 lo[kQBatch][2], hi[kQBatch][2], cs[kQBatch][4];
 #pragma unroll
         for (int b = 0; b < kQBatch; b++) {
-            const int i = min(i0 + b * kFtcThreads, kQPieces - 1);
-            const int r = i / (HD / 8), c8 = i % (HD / 8);            // row 0..255, 16-byte piece (8 dims)
-            const int row = tile.row0 + min(r, tile.n_rows - 1);      // rows past the tile repeat the last row
-            const float4* src = reinterpret_cast<const float4*>(a.qkv + static_cast<size_t>(row) * a.ld + head * HD + c8 * 8);
-            x[b] = ldg_f4_early(src);
-            y[b] = ldg_f4_early(src + 1);
+            const int i = min(i0 + b * kFtcThreads, kQItems - 1);
+            const int r = i / (HD / 16), c8 = i % (HD / 16);                 // row 0..255, 8-dim piece of the lower half
+            const int rc = min(r, tile.n_rows - 1);                          // rows past the tile repeat the last row
+            const float4* src = reinterpret_cast<const float4*>(a.qkv + static_cast<size_t>(tile.row0 + rc) * a.ld + head * HD + c8 * 8);
+            const float4* csp = reinterpret_cast<const float4*>(a.rope + static_cast<size_t>(tile.pos0 + rc) * HD + c8 * 16);
+            lo[b][0] = ldg_f4_early(src); lo[b][1] = ldg_f4_early(src + 1);
+            hi[b][0] = ldg_f4_early(src + HD / 8); hi[b][1] = ldg_f4_early(src + HD / 8 + 1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) cs[b][k] = ldg_f4_early(csp + k);
         }
 #pragma unroll
         for (int b = 0; b < kQBatch; b++) {
             const int i = i0 + b * kFtcThreads;
-            if (i < kQPieces) {
-                const uint32_t r = i / (HD / 8), c8 = i % (HD / 8);
-                const uint32_t t = r >> 7, rr = r & 127, panel = c8 >> 3, piece = c8 & 7;
-                const uint32_t dst = sQ + t * kTileBytes + panel * kPanelBytes + rr * 128 + ((piece ^ (rr & 7)) << 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(x[b].x, x[b].y)), "r"(pack_bf16x2(x[b].z, x[b].w)),
-                             "r"(pack_bf16x2(y[b].x, y[b].y)), "r"(pack_bf16x2(y[b].z, y[b].w)) : "memory");
+            if (i < kQItems) {
+                const uint32_t r = i / (HD / 16), c8 = i % (HD / 16);
+                const float x0[8] = {lo[b][0].x, lo[b][0].y, lo[b][0].z, lo[b][0].w, lo[b][1].x, lo[b][1].y, lo[b][1].z, lo[b][1].w};
+                const float x1[8] = {hi[b][0].x, hi[b][0].y, hi[b][0].z, hi[b][0].w, hi[b][1].x, hi[b][1].y, hi[b][1].z, hi[b][1].w};
+                const float cc[8] = {cs[b][0].x, cs[b][0].z, cs[b][1].x, cs[b][1].z, cs[b][2].x, cs[b][2].z, cs[b][3].x, cs[b][3].z};
+                const float ss[8] = {cs[b][0].y, cs[b][0].w, cs[b][1].y, cs[b][1].w, cs[b][2].y, cs[b][2].w, cs[b][3].y, cs[b][3].w};
+                float y0[8], y1[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    y0[e] = x0[e] * cc[e] - x1[e] * ss[e];
+                    y1[e] = x1[e] * cc[e] + x0[e] * ss[e];
+                }
+                const uint32_t t = r >> 7, rr = r & 127;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float* y = h ? y1 : y0;
+                    const uint32_t c8h = c8 + h * (HD / 16), panel = c8h >> 3, piece = c8h & 7;
+                    const uint32_t dst = sQ + t * kTileBytes + panel * kPanelBytes + rr * 128 + ((piece ^ (rr & 7)) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pack_bf16x2(y[0], y[1])), "r"(pack_bf16x2(y[2], y[3])),
+                                 "r"(pack_bf16x2(y[4], y[5])), "r"(pack_bf16x2(y[6], y[7])) : "memory");
+                }
             }
         }
     }
