@@ -570,8 +570,20 @@ __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const uint16_t*
     __shared__ float s_red[32];
     const int r = blockIdx.x;
     const float* xr = x + static_cast<size_t>(r) * H;
+    // the row stays in registers between the two passes (up to 8 float4 per thread: H <= 8192 with 256 threads); all loads of a
+    // thread are in flight together
+    constexpr int kCache = 8;
+    float4 cache[kCache];
+    const int stride = blockDim.x * 4;
+#pragma unroll
+    for (int k = 0; k < kCache; k++) {
+        const int i = threadIdx.x * 4 + k * stride;
+        cache[k] = i < H ? *reinterpret_cast<const float4*>(xr + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     float ss = 0.f;
-    for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
+#pragma unroll
+    for (int k = 0; k < kCache; k++) ss += cache[k].x * cache[k].x + cache[k].y * cache[k].y + cache[k].z * cache[k].z + cache[k].w * cache[k].w;
+    for (int i = threadIdx.x * 4 + kCache * stride; i < H; i += stride) {
         const float4 v = *reinterpret_cast<const float4*>(xr + i);
         ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
@@ -581,14 +593,19 @@ __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const uint16_t*
     float tot = 0.f;
     for (int i = 0; i < (blockDim.x >> 5); i++) tot += s_red[i];
     const float inv = rsqrtf(tot / static_cast<float>(H) + eps);
-    for (int i = threadIdx.x * 4; i < H; i += blockDim.x * 4) {
-        const float4 v = *reinterpret_cast<const float4*>(xr + i);
+    auto emit = [&](int i, const float4& v) {
         const uint2 nw = *reinterpret_cast<const uint2*>(w + i);
         uint2 o;
         o.x = pack_bf16x2(bf16lo(nw.x) * (v.x * inv), bf16hi(nw.x) * (v.y * inv));
         o.y = pack_bf16x2(bf16lo(nw.y) * (v.z * inv), bf16hi(nw.y) * (v.w * inv));
         *reinterpret_cast<uint2*>(y + static_cast<size_t>(r) * H + i) = o;
+    };
+#pragma unroll
+    for (int k = 0; k < kCache; k++) {
+        const int i = threadIdx.x * 4 + k * stride;
+        if (i < H) emit(i, cache[k]);
     }
+    for (int i = threadIdx.x * 4 + kCache * stride; i < H; i += stride) emit(i, *reinterpret_cast<const float4*>(xr + i));
 }
 
 // prefill: fp32 -> bf16 (attention output -> A operand of the O projection)
