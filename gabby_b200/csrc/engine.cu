@@ -947,7 +947,7 @@ void mega_enqueue(b2l_ctx* c, int n_steps, bool host_io = false) {
     a.attn_tps = c->mega_attn_tps;
     a.attn_max_splits = std::getenv("B2L_MEGA_MAXSPLIT") ? std::max(1, std::atoi(std::getenv("B2L_MEGA_MAXSPLIT"))) : 16;
     a.attn_qhead_tokens = std::getenv("B2L_MEGA_QHEAD_TOK") ? std::max(32, std::atoi(std::getenv("B2L_MEGA_QHEAD_TOK"))) : 512;   // measured on the 8B TP=8 rank shapes at context 4096: 16 / 512 -> 0.99 ms, 8 / 256 -> 1.80 ms
-    a.l2_ahead = std::getenv("B2L_MEGA_L2AHEAD") ? std::atoi(std::getenv("B2L_MEGA_L2AHEAD")) : 8;   // measured: 8 chunks (19 MB chip-wide) -4.5 %, 32 chunks +9 % (L2 thrash)
+    a.l2_ahead = std::getenv("B2L_MEGA_L2AHEAD") ? std::atoi(std::getenv("B2L_MEGA_L2AHEAD")) : 6;   // measured (profiles/r02_megakernel_knob_sweeps.txt): 6 chunks (14 MB chip-wide) best, 8 +1.2 %, 12 +4 %, 32 +9 % (L2 thrash)
     a.producer_sleep_ns = std::getenv("B2L_MEGA_PSLEEP") ? std::atoi(std::getenv("B2L_MEGA_PSLEEP")) : 100;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c->prop.multiProcessorCount);
