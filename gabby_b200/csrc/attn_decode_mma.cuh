@@ -13,11 +13,13 @@
 
 namespace b2l {
 
-template <int HD>
-constexpr size_t attn_mma_smem() { return static_cast<size_t>(kAttnWarps) * 2 * 2 * 16 * (HD + 8) * sizeof(uint16_t); }
+// NBUF tile buffers per warp: NBUF - 1 tiles (K + V, 16 tokens each) are in flight while one is multiplied
+template <int HD, int NBUF = 2>
+constexpr size_t attn_mma_smem() { return static_cast<size_t>(kAttnWarps) * NBUF * 2 * 16 * (HD + 8) * sizeof(uint16_t); }
 
-template <int HD, int GROUP>
-__global__ void __launch_bounds__(kAttnThreads) attn_decode_mma_kernel(const AttnArgs a) {
+// three CTAs per SM with two buffers (the third needs <= 168 registers: ncu showed 169 and two resident CTAs, 1.5 waves)
+template <int HD, int GROUP, int NBUF = 2>
+__global__ void __launch_bounds__(kAttnThreads, NBUF == 2 ? 3 : 2) attn_decode_mma_kernel(const AttnArgs a) {
     static_assert(GROUP <= 8, "query heads per kv head are the (padded) 16 MMA rows; rows 8..15 stay empty");
     constexpr int LDS = HD + 8;                 // padded tile row (bf16): kills ldmatrix bank conflicts
     constexpr int KSTEPS = HD / 16, DBLOCKS = HD / 8, TILE = 16;
@@ -36,11 +38,14 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_mma_kernel(const Att
     if (split >= eff) return;
     // splits start on 16-token boundaries: with page_size % 16 == 0 a warp tile then lies inside ONE page (one block
     // table lookup per tile, rows at a fixed stride -- the per-token page arithmetic was most of the instruction count)
+    // a.interleave: the 16-token tiles of the whole context are dealt round-robin to the eff x 4 warps of this (row, kv head),
+    // so every warp of every split gets the same number of tiles to within one (contiguous chunks per split leave the warps
+    // of a CTA with 4 or 5 tiles when the chunk is not a multiple of 64 tokens, and the last split short)
     const int chunk = (((ctx + eff - 1) / eff) + TILE - 1) / TILE * TILE;
-    const int j0 = split * chunk, j1 = min(ctx, j0 + chunk);
+    const int j0 = a.interleave ? 0 : split * chunk, j1 = a.interleave ? ctx : min(ctx, j0 + chunk);
     const bool page_tiles = (a.kv.page_size % TILE) == 0;
     const int32_t* bt = a.rm.block_tables + static_cast<size_t>(a.rm.slots[r]) * a.rm.max_blocks;
-    uint16_t* my_tiles = asm_tiles + static_cast<size_t>(warp) * 4 * TILE_ELEMS;
+    uint16_t* my_tiles = asm_tiles + static_cast<size_t>(warp) * NBUF * 2 * TILE_ELEMS;
 
     // ---- Q fragments (A operand): row gid = query head gid of this kv head, rows 8..15 are padding ----
     uint32_t qhi[KSTEPS][2], qlo[KSTEPS][2];   // a0 (k = tig*2, +1) and a2 (k + 8) of each k-step; a1 = a3 = 0
@@ -91,22 +96,36 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_mma_kernel(const Att
     for (int d = 0; d < DBLOCKS; d++) o[d][0] = o[d][1] = 0.f;
     float m = -INFINITY, l = 0.f;   // running max / (quad-partial) sum of row gid
 
-    const int first = j0 + warp * TILE, stride = kAttnWarps * TILE;
+    const int first = a.interleave ? (split * kAttnWarps + warp) * TILE : j0 + warp * TILE;
+    const int stride = (a.interleave ? eff : 1) * kAttnWarps * TILE;
     int buf = 0;
-    if (first < j1) issue_tile(first, 0);
+    // prologue: NBUF - 1 tiles in flight (one commit group per tile slot, empty groups past the end keep the count uniform)
+#pragma unroll
+    for (int i = 0; i < NBUF - 1; i++) {
+        if (first + i * stride < j1) issue_tile(first + i * stride, i);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int jt = first; jt < j1; jt += stride) {
-        const bool more = jt + stride < j1;
-        if (more) issue_tile(jt + stride, buf ^ 1);
-        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        {
+            const int nxt = jt + (NBUF - 1) * stride;
+            int nb_ = buf + NBUF - 1;
+            if (nb_ >= NBUF) nb_ -= NBUF;
+            if (nxt < j1) issue_tile(nxt, nb_);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(NBUF - 1) : "memory");   // all but the NBUF - 1 newest groups: this tile has landed
         __syncwarp();
         const uint16_t* sK = my_tiles + buf * 2 * TILE_ELEMS;
         const uint16_t* sV = sK + TILE_ELEMS;
 
         // ---- S = Q K^T : 16 (heads) x 16 (tokens); hi and lo parts of q accumulate into the same tile ----
+        // (the hi and the lo products run as separate accumulation chains, four independent chains of KSTEPS MMAs per
+        // tile instead of two of 2 KSTEPS: with 2-3 warps per scheduler the dependent-issue latency of mma.sync was
+        // a quarter of the stall samples)
         float s[2][4];
 #pragma unroll
         for (int nb = 0; nb < 2; nb++) {
+            float sl[4] = {0.f, 0.f, 0.f, 0.f};
             s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
 #pragma unroll
             for (int k2 = 0; k2 < KSTEPS / 2; k2++) {
@@ -115,10 +134,12 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_mma_kernel(const Att
                 const uint32_t ah0[4] = {qhi[2 * k2][0], 0u, qhi[2 * k2][1], 0u}, ah1[4] = {qhi[2 * k2 + 1][0], 0u, qhi[2 * k2 + 1][1], 0u};
                 const uint32_t al0[4] = {qlo[2 * k2][0], 0u, qlo[2 * k2][1], 0u}, al1[4] = {qlo[2 * k2 + 1][0], 0u, qlo[2 * k2 + 1][1], 0u};
                 mma_bf16_16816(s[nb], ah0, kf[0], kf[1]);
+                mma_bf16_16816(sl, al0, kf[0], kf[1]);
                 mma_bf16_16816(s[nb], ah1, kf[2], kf[3]);
-                mma_bf16_16816(s[nb], al0, kf[0], kf[1]);
-                mma_bf16_16816(s[nb], al1, kf[2], kf[3]);
+                mma_bf16_16816(sl, al1, kf[2], kf[3]);
             }
+            s[nb][0] += sl[0];
+            s[nb][1] += sl[1];
         }
         // ---- online softmax of row gid over the tile's 16 tokens (4 of them in this thread) ----
         float mx = m;
@@ -173,8 +194,9 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_mma_kernel(const Att
             o[2 * d2 + 1][0] = acc1[0]; o[2 * d2 + 1][1] = acc1[1];
         }
         __syncwarp();   // the tile may be overwritten by the next iteration's cp.async
-        buf ^= 1;
+        if (++buf == NBUF) buf = 0;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
 

@@ -69,4 +69,29 @@ __device__ __forceinline__ int argmax_key_index(unsigned long long k) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Thread-block clusters: rank, cluster-wide barrier (release / acquire), loads from a peer CTA's shared memory (DSMEM)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem_ptr, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(local_smem_ptr))), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ float dsmem_ld_f32(const float* local_smem_ptr, uint32_t rank) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(dsmem_addr(local_smem_ptr, rank)) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long dsmem_ld_u64(const unsigned long long* local_smem_ptr, uint32_t rank) {
+    unsigned long long v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(dsmem_addr(local_smem_ptr, rank)) : "memory");
+    return v;
+}
+
 }  // namespace b2l

@@ -129,12 +129,14 @@ T* dalloc(b2l_ctx* c, size_t n) {
 
 // The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: remember which
 // (kernel, device) pairs have it, so that a context on a second GPU of the same process gets it too.
-void ensure_smem_optin(const void* kern, int device, size_t bytes) {
+void ensure_smem_optin(const void* kern, int device, size_t bytes, bool max_carveout = false) {
     static std::mutex mu;
     static std::set<std::pair<const void*, int>> done;
     std::lock_guard<std::mutex> lock(mu);
     if (done.count({kern, device})) return;
     B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    // several CTAs per SM only fit when the SM is carved for shared memory (the driver's default guess can stop one short)
+    if (max_carveout) B2L_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     done.insert({kern, device});
 }
 
@@ -207,6 +209,27 @@ void launch(b2l_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t 
     c->launched++;
 }
 
+// the same with a thread-block cluster of (cluster_x, 1, 1)
+template <typename... KArgs, typename... Args>
+void launch_cluster(b2l_ctx* c, void (*kernel)(KArgs...), dim3 grid, dim3 block, unsigned cluster_x, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    B2L_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    c->launched++;
+}
+
 constexpr size_t kGemvSmemBudget = 32 * 1024;  // x tile per CTA: small enough for 6+ CTAs per SM at batch 8
 
 int gemv_kt(int B, int K) {
@@ -266,6 +289,10 @@ void gemv(b2l_ctx* c, const uint16_t* W, const float* x, int ldx, float* y, int 
     }
 }
 
+// tile buffers per warp of the tensor-core decode attention: 3 = two tiles in flight (ncu, 3B batch 8 context 2048, 4 splits:
+// 24.7 us per launch against 26.2 with 2 buffers; 6-7 splits 28.6-32 us -- profiles/r02_attn_decode_sweeps.txt)
+constexpr int kAttnNbufDefault = 3;
+
 template <int HD>
 void attn_launch_hd(b2l_ctx* c, const AttnArgs& a, int R) {
     // about four 128-thread CTAs per SM when the context is long (measured in one run, 3B batch 8, context 2048:
@@ -278,19 +305,37 @@ void attn_launch_hd(b2l_ctx* c, const AttnArgs& a, int R) {
     static const bool use_mma = !(std::getenv("B2L_ATTN_MMA") && std::atoi(std::getenv("B2L_ATTN_MMA")) == 0);
     if constexpr (HD >= 64) {
         if (use_mma) {   // tensor-core kernel (attn_decode_mma.cuh); B2L_ATTN_MMA=0 selects the CUDA-core kernel
-            constexpr size_t smem = attn_mma_smem<HD>();
-            auto go = [&](auto kern) {
-                ensure_smem_optin(reinterpret_cast<const void*>(kern), c->p.device, smem);
-                launch(c, kern, grid, block, smem, a);
+            // tuning knobs: B2L_ATTN_NBUF=3: two tiles in flight per warp (2 CTAs per SM at head_dim 128 instead of 3);
+            // B2L_ATTN_INTERLEAVE=0: contiguous context chunks per split
+            static const int nbuf = std::getenv("B2L_ATTN_NBUF") ? std::atoi(std::getenv("B2L_ATTN_NBUF")) : kAttnNbufDefault;
+            static const bool interleave = !(std::getenv("B2L_ATTN_INTERLEAVE") && std::atoi(std::getenv("B2L_ATTN_INTERLEAVE")) == 0);
+            AttnArgs ai = a;
+            ai.interleave = interleave ? 1 : 0;
+            auto go = [&](auto kern, size_t smem) {
+                ensure_smem_optin(reinterpret_cast<const void*>(kern), c->p.device, smem, true);
+                // one wave: as many context splits as keep every CTA resident at once. ncu showed the old fixed guess (3 CTAs per
+                // SM -> 7 splits at 3B batch 8 = 448 CTAs) running as 1.5 waves of the 2 CTAs per SM that really fit; every CTA
+                // also pays ~6 us of fixed latency (block table -> first tile, CTA merge, fence + last-arriver merge), so fewer,
+                // longer CTAs win: 4 splits 2.58-2.63 ms/step, 7 splits 2.83-2.91
+                int occ = 0;
+                B2L_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kAttnThreads, smem));
+                const int one_wave = std::max(1, std::min(32, occ * c->prop.multiProcessorCount / (c->nkv_l * R)));
+                const dim3 g(std::max(1, std::min(c->nsplit, forced > 0 ? forced : one_wave)), c->nkv_l, R);
+                launch(c, kern, g, block, smem, ai);
             };
+#define B2L_ATTN_GO(G)                                                                                   \
+    if (nbuf == 3) go(attn_decode_mma_kernel<HD, G, 3>, attn_mma_smem<HD, 3>());                             \
+    else go(attn_decode_mma_kernel<HD, G, 2>, attn_mma_smem<HD, 2>());                                       \
+    return;
             switch (c->group) {
-                case 1: go(attn_decode_mma_kernel<HD, 1>); return;
-                case 2: go(attn_decode_mma_kernel<HD, 2>); return;
-                case 3: go(attn_decode_mma_kernel<HD, 3>); return;
-                case 4: go(attn_decode_mma_kernel<HD, 4>); return;
-                case 8: go(attn_decode_mma_kernel<HD, 8>); return;
+                case 1: B2L_ATTN_GO(1)
+                case 2: B2L_ATTN_GO(2)
+                case 3: B2L_ATTN_GO(3)
+                case 4: B2L_ATTN_GO(4)
+                case 8: B2L_ATTN_GO(8)
                 default: throw Error("unsupported GQA group size (heads per kv head must be 1,2,3,4 or 8)");
             }
+#undef B2L_ATTN_GO
         }
     }
     switch (c->group) {
@@ -339,13 +384,24 @@ void skinny_setup(b2l_ctx* c) {
     B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(skinny_smem(32))));
     B2L_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(skinny_smem(64))));
     c->skinny_ok = true;
+    // fused epilogues of the batched path (on by default; the switches are for A/B measurements)
+    c->rope_fuse = !(std::getenv("B2L_ROPE_FUSE") && std::atoi(std::getenv("B2L_ROPE_FUSE")) == 0);
+    c->norm_cluster = !(std::getenv("B2L_NORM_CLUSTER") && std::atoi(std::getenv("B2L_NORM_CLUSTER")) == 0);
 }
+
+struct RopeKvFuse {   // what rope_kv_kernel needs, for the QKV projection's fused epilogue (skinny_reduce_rope_kv_kernel)
+    const float* rope;
+    KvLayout kv;
+    RowMeta rm;
+    int nh, nkv, hd;
+};
 
 // y (op)= W x for R >= 2 activation rows, 32 rows per pass: prep (hi/lo bf16 [+ RMSNorm]) -> tcgen05 skinny GEMM -> split
 // reduce + epilogue
 void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, int ldx, const uint16_t* norm_w, uint16_t* xbuf,
                    float* y, int ldy, int mode, int R_all, const TpSend* tps = nullptr, bool x_presplit = false,
-                   uint16_t* split_next = nullptr, const uint16_t* next_norm = nullptr) {
+                   uint16_t* split_next = nullptr, const uint16_t* next_norm = nullptr, const RopeKvFuse* rope_kv = nullptr) {
+    // rope_kv (mode 0, the QKV projection): the K-split reduce also rotates q / k and appends k, v to the paged cache
     // next_norm (mode 1, R_all <= 32, N <= 8192): the residual update is fused with RMSNorm(next_norm) + hi/lo split into split_next
     // x_presplit: the producer of x already wrote the bf16 hi/lo rows into xbuf (R_all <= 32 only)
     // split_next (mode 2 only): write the SwiGLU output as bf16 hi/lo rows for the next projection instead of fp32
@@ -372,8 +428,20 @@ void skinny_linear(b2l_ctx* c, const uint16_t* W, int N, int K, const float* x, 
         TpSend send = tps ? *tps : TpSend{};
         for (int p = 0; p < send.tp; p++) send.dst[p] += static_cast<size_t>(r0) * ldy;
         if (mode == 1 && next_norm && split_next) {
-            launch(c, skinny_reduce_norm_split_kernel, dim3(R), dim3(1024), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, yg, next_norm, split_next,
-                   c->p.rms_norm_eps);
+            // a cluster of CTAs per row (B2L_NORM_CLUSTER=0: the one-CTA-per-row kernel)
+            if (c->norm_cluster)
+                launch_cluster(c, skinny_reduce_norm_split_cluster_kernel, dim3(kNormCluster, R), dim3(kNormThreads), kNormCluster,
+                               static_cast<const float*>(c->sk_partial), ksplit, T, N, yg, next_norm, split_next, c->p.rms_norm_eps);
+            else
+                launch(c, skinny_reduce_norm_split_kernel, dim3(R), dim3(1024), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, yg, next_norm, split_next,
+                       c->p.rms_norm_eps);
+            continue;
+        }
+        if (mode == 0 && rope_kv) {
+            const RopeKvFuse& f = *rope_kv;
+            const RowMeta rm{f.rm.positions + r0, f.rm.slots + r0, f.rm.block_tables, f.rm.max_blocks};
+            launch(c, skinny_reduce_rope_kv_kernel, dim3(f.nh + 2 * f.nkv, R), dim3(f.hd / 2), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, yg, ldy,
+                   f.rope, f.kv, rm, f.nh, f.nkv, f.hd);
             continue;
         }
         launch(c, skinny_reduce_kernel, dim3((cols + 255) / 256, R), dim3(256), 0, static_cast<const float*>(c->sk_partial), ksplit, T, N, R, mode, yg, ldy, send,
@@ -483,10 +551,12 @@ void tp_allreduce_add(b2l_ctx* c, int R) {
 // greedy argmax over vocab-sharded logits: local (max, global index), all-gather, first-max merge
 void tp_argmax(b2l_ctx* c, const float* logits, int R) {
     if (c->p.tp_size == 1) {
-        launch(c, argmax_kernel, dim3(R), dim3(1024), 0, logits, c->V_l, c->V_l, 0, c->d_next_ids, static_cast<float*>(nullptr));
+        launch_cluster(c, argmax_cluster_kernel, dim3(kArgmaxCluster, R), dim3(1024), kArgmaxCluster, logits, c->V_l, c->V_l, 0, c->d_next_ids,
+                       static_cast<float*>(nullptr));
         return;
     }
-    launch(c, argmax_kernel, dim3(R), dim3(1024), 0, logits, c->V_l, c->V_l, c->p.tp_rank * c->V_l, c->d_next_ids, c->tp_vals);
+    launch_cluster(c, argmax_cluster_kernel, dim3(kArgmaxCluster, R), dim3(1024), kArgmaxCluster, logits, c->V_l, c->V_l, c->p.tp_rank * c->V_l,
+                   c->d_next_ids, c->tp_vals);
     launch(c, tp_pack_kernel, dim3(1), dim3(64), 0, static_cast<const float*>(c->tp_vals), static_cast<const int32_t*>(c->d_next_ids), c->tp_pack, R);
     B2L_NCCL(nccl().AllGather(c->tp_pack, c->tp_gather, static_cast<size_t>(c->max_rows) * 2, kNcclFloat32, c->nccl_comm, c->stream));
     launch(c, tp_merge_kernel, dim3(1), dim3(64), 0, static_cast<const float*>(c->tp_gather), c->d_next_ids, R, c->max_rows, c->p.tp_size);
@@ -505,9 +575,13 @@ void enqueue_forward(b2l_ctx* c, int R, bool want_logits, int tap_row0) {
         const bool sk = c->skinny_ok && R >= 2;   // batched decode: projections on the tensor cores
         // single GPU, one row group: the residual epilogues of O and down also produce the next projection's normalised operand
         const bool fuse_norm = sk && R <= 32 && c->p.tp_size == 1 && c->H <= 8192;
-        if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R, nullptr, fuse_norm && l > 0);
+        // batched decode: the QKV projection's split-K reduce rotates q / k and appends k, v itself (B2L_ROPE_FUSE=0: separate kernels)
+        const bool rope_fused = sk && c->rope_fuse;
+        const RopeKvFuse rkf{c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd};
+        if (sk) skinny_linear(c, w.w_qkv, c->qkv_l, c->H, c->h, c->H, w.in_norm, c->sk_xh, c->qkv, c->qkv_l, 0, R, nullptr, fuse_norm && l > 0, nullptr, nullptr,
+                              rope_fused ? &rkf : nullptr);
         else gemv(c, w.w_qkv, c->h, c->H, c->qkv, c->qkv_l, w.in_norm, c->qkv_l, c->H, 0, R);
-        launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd, 0);
+        if (!rope_fused) launch(c, rope_kv_kernel, dim3(R), dim3(256), 0, c->qkv, c->qkv_l, c->rope, kv, rm, c->nh_l, c->nkv_l, c->hd, 0);
         const bool fuse = sk && R <= 32;   // one row group: producers write the next projection's bf16 hi/lo operand directly
         const int skT = R <= 8 ? 8 : R <= 16 ? 16 : 32;
         AttnArgs aa{c->qkv, c->qkv_l, kv, rm, c->part_acc, c->part_ml, c->attn_counters, c->attn, c->qd_l, scale};
@@ -1747,8 +1821,20 @@ int b2l_op_argmax(int device, const float* x, int B, int N, int32_t* out) {
         float* dx = dalloc<float>(c, static_cast<size_t>(B) * N);
         int32_t* di = dalloc<int32_t>(c, B);
         B2L_CUDA(cudaMemcpy(dx, x, sizeof(float) * B * N, cudaMemcpyHostToDevice));
-        launch(c, argmax_kernel, dim3(B), dim3(1024), 0, static_cast<const float*>(dx), N, N, 0, di, static_cast<float*>(nullptr));
+        // the engine's kernel (cluster of CTAs per row); rows of the second half of the batch also go through the one-CTA kernel
+        // it replaced, which stays as the reference of the first-max rule
+        launch_cluster(c, argmax_cluster_kernel, dim3(kArgmaxCluster, B), dim3(1024), kArgmaxCluster, static_cast<const float*>(dx), N, N, 0, di,
+                       static_cast<float*>(nullptr));
         B2L_CUDA(cudaStreamSynchronize(c->stream));
+        {
+            std::vector<int32_t> a(B), b(B);
+            int32_t* dj = dalloc<int32_t>(c, B);
+            launch(c, argmax_kernel, dim3(B), dim3(1024), 0, static_cast<const float*>(dx), N, N, 0, dj, static_cast<float*>(nullptr));
+            B2L_CUDA(cudaStreamSynchronize(c->stream));
+            B2L_CUDA(cudaMemcpy(a.data(), di, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+            B2L_CUDA(cudaMemcpy(b.data(), dj, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
+            B2L_CHECK(a == b, "argmax: cluster kernel and one-CTA kernel disagree");
+        }
         B2L_CUDA(cudaMemcpy(out, di, sizeof(int32_t) * B, cudaMemcpyDeviceToHost));
     });
 }

@@ -126,6 +126,8 @@ struct b2l_ctx {
 
     // batched decode on the tensor cores (skinny_gemm.cuh)
     bool skinny_ok = false;
+    bool rope_fuse = false;      // QKV split-K reduce also applies RoPE and appends k, v (skinny_reduce_rope_kv_kernel)
+    bool norm_cluster = false;   // residual + RMSNorm + hi/lo split epilogue on a cluster per row
     uint16_t *sk_xh = nullptr, *sk_xq = nullptr, *sk_xi = nullptr;   // bf16 hi/lo activation rows [32][K]
     float* sk_partial = nullptr;                                       // [ksplit][16][N] fp32
     size_t sk_partial_floats = 0;

@@ -160,6 +160,46 @@ __global__ void skinny_reduce_kernel(const float* __restrict__ partial, int kspl
     }
 }
 
+// QKV projection epilogue fused with RoPE and the K/V append: sums the K splits of one head of one activation row, rotates
+// the q / k heads (rotate-half pairs j, j + hd/2), stores q as fp32 into qkv (what the attention kernels read) and k, v as
+// bf16 into the row's page of the cache. Replaces skinny_reduce_kernel(mode 0) + rope_kv_kernel: one launch instead of
+// two, and (heads x rows) CTAs instead of rope_kv_kernel's one CTA per row. grid (nh + 2 nkv, R), hd / 2 threads.
+// Same arithmetic, in the same order, as the two kernels it replaces (sum over splits in split order, then the rotation).
+__global__ void skinny_reduce_rope_kv_kernel(const float* __restrict__ partial, int ksplit, int T, int N, float* __restrict__ qkv, int ld,
+                                             const float* __restrict__ rope, KvLayout kv, RowMeta rm, int nh, int nkv, int hd) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int head = blockIdx.x, r = blockIdx.y, j = threadIdx.x, half = hd >> 1;
+    const int pos = rm.positions[r];
+    const int c0 = head * hd + j, c1 = c0 + half;   // q heads, k heads, v heads are contiguous in the fused row
+    float x0 = 0.f, x1 = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < ksplit; s++) {
+        const float* p = partial + (static_cast<size_t>(s) * T + r) * N;
+        x0 += p[c0];
+        x1 += p[c1];
+    }
+    if (head < nh) {
+        const float c = rope[static_cast<size_t>(pos) * hd + 2 * j], s = rope[static_cast<size_t>(pos) * hd + 2 * j + 1];
+        float* row = qkv + static_cast<size_t>(r) * ld;
+        row[c0] = x0 * c - x1 * s;
+        row[c1] = x1 * c + x0 * s;
+        return;
+    }
+    const int page = rm.block_tables[static_cast<size_t>(rm.slots[r]) * rm.max_blocks + pos / kv.page_size];
+    const int off = pos % kv.page_size;
+    if (head < nh + nkv) {
+        const float c = rope[static_cast<size_t>(pos) * hd + 2 * j], s = rope[static_cast<size_t>(pos) * hd + 2 * j + 1];
+        uint16_t* kdst = kv.at(page, 0, off) + (head - nh) * hd;
+        kdst[j] = f32_to_bf16_bits(x0 * c - x1 * s);
+        kdst[j + half] = f32_to_bf16_bits(x1 * c + x0 * s);
+    } else {
+        uint16_t* vdst = kv.at(page, 1, off) + (head - nh - nkv) * hd;
+        vdst[j] = f32_to_bf16_bits(x0);
+        vdst[j + half] = f32_to_bf16_bits(x1);
+    }
+}
+
 // Row-parallel projection epilogue fused with the NEXT projection's prologue: h[r] += sum over K splits of partial,
 // then RMSNorm(h[r]) * norm_w -> bf16 hi/lo rows of the next B operand. One CTA per activation row (the norm needs the
 // whole row); replaces skinny_reduce_kernel(mode 1) + split_bf16_kernel<true>.
@@ -210,6 +250,75 @@ __global__ void __launch_bounds__(1024) skinny_reduce_norm_split_kernel(const fl
             *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(T + r) * N + n) = pack_bf16x2(y0 - bf16_bits_to_f32(h0), y1 - bf16_bits_to_f32(h1));
         }
     }
+}
+
+// The same epilogue spread over a thread-block CLUSTER per activation row: the one-CTA-per-row kernel above leaves 8 CTAs
+// (batch 8) to pull ksplit x N partial sums through L2 one dependent load after the other (ncu: 11 us per launch, twice per
+// layer). Here CTA `rank` of a cluster of kNormCluster owns columns [rank * cols, (rank + 1) * cols) of its row, keeps
+// its updated h values in registers, and the row's sum of squares is exchanged through distributed shared memory
+// (one float per CTA, summed in rank order by everybody: all CTAs get the identical 1/rms). grid (kNormCluster, R).
+constexpr int kNormCluster = 8, kNormThreads = 256;
+__global__ void __launch_bounds__(kNormThreads) skinny_reduce_norm_split_cluster_kernel(const float* __restrict__ partial, int ksplit, int T, int N,
+                                                                                        float* __restrict__ h, const uint16_t* __restrict__ norm_w,
+                                                                                        uint16_t* __restrict__ out, float eps) {
+    __shared__ float s_red[kNormThreads / 32];
+    __shared__ float s_cta_total;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = blockIdx.y, tid = threadIdx.x;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const int cols = ((N / 2 + kNormCluster - 1) / kNormCluster) * 2;   // even column count per CTA
+    const int c_lo = rank * cols, c_hi = min(N, c_lo + cols);
+    constexpr int kMaxIter = 2;   // N <= 8192: <= 1024 columns per CTA
+    float2 v[kMaxIter];
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < kMaxIter; it++) {
+        const int n = c_lo + it * 2 * kNormThreads + tid * 2;
+        v[it] = make_float2(0.f, 0.f);
+        if (n < c_hi) {
+            float a0 = 0.f, a1 = 0.f;
+            const float* p = partial + static_cast<size_t>(r) * N + n;
+            const size_t stride = static_cast<size_t>(T) * N;
+#pragma unroll 4
+            for (int s = 0; s < ksplit; s++) {
+                const float2 q = *reinterpret_cast<const float2*>(p + s * stride);
+                a0 += q.x;
+                a1 += q.y;
+            }
+            float2* hp = reinterpret_cast<float2*>(h + static_cast<size_t>(r) * N + n);
+            float2 cur = *hp;
+            cur.x += a0;
+            cur.y += a1;
+            *hp = cur;
+            v[it] = cur;
+            ss += cur.x * cur.x + cur.y * cur.y;
+        }
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kNormThreads / 32; i++) t += s_red[i];
+        s_cta_total = t;
+    }
+    cluster_sync_all();   // every CTA's total is published (release / acquire at cluster scope)
+    float tot = 0.f;
+    for (int q = 0; q < kNormCluster; q++) tot += dsmem_ld_f32(&s_cta_total, static_cast<uint32_t>(q));
+    const float inv = rsqrtf(tot / static_cast<float>(N) + eps);
+#pragma unroll
+    for (int it = 0; it < kMaxIter; it++) {
+        const int n = c_lo + it * 2 * kNormThreads + tid * 2;
+        if (n < c_hi) {
+            const uint32_t nw = *reinterpret_cast<const uint32_t*>(norm_w + n);
+            const float y0 = bf16lo(nw) * (v[it].x * inv), y1 = bf16hi(nw) * (v[it].y * inv);
+            const uint16_t h0 = f32_to_bf16_bits(y0), h1 = f32_to_bf16_bits(y1);
+            *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(r) * N + n) = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
+            *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(T + r) * N + n) = pack_bf16x2(y0 - bf16_bits_to_f32(h0), y1 - bf16_bits_to_f32(h1));
+        }
+    }
+    cluster_sync_all();   // nobody exits while a peer may still read its shared memory
 }
 
 // fp32 rows -> bf16 (hi, lo) rows for the B operand; NORM: fused RMSNorm. out is [2*T][K]: row r = hi, row T + r = lo

@@ -83,6 +83,10 @@ def test_argmax_first_max_and_edge_values():
     rng = np.random.default_rng(0)
     y = rng.standard_normal((8, 50001)).astype(np.float32)
     assert np.array_equal(_capi().op_argmax(y), y.argmax(axis=1).astype(np.int32))
+    # fewer columns than the cluster has CTAs (empty slices), and a row length that is not a multiple of anything
+    for n in (1, 5, 1031):
+        z = rng.standard_normal((3, n)).astype(np.float32)
+        assert np.array_equal(_capi().op_argmax(z), z.argmax(axis=1).astype(np.int32)), n
 
 
 # ---------------------------------------------------------------------------------------------
@@ -186,9 +190,10 @@ def test_batched_decode_ragged_lengths_matches_per_sequence_oracle():
         assert ids[:, i].tolist() == oids[1:].tolist(), (i, float(margins.min()))
 
 
-@pytest.mark.parametrize("n_seq", [5, 12, 20])
+@pytest.mark.parametrize("n_seq", [5, 12, 20, 40])
 def test_batched_decode_on_tensor_cores_matches_per_sequence_oracle(n_seq):
-    """2..16 rows per step: projections run as tcgen05 skinny GEMMs (hi/lo bf16 split of the fp32 activations)."""
+    """2..64 rows per step: projections run as tcgen05 skinny GEMMs (hi/lo bf16 split of the fp32 activations); 40 rows =
+    two row groups (32 + 8): the fused QKV-reduce + RoPE + KV-append epilogue with a row offset."""
     po = _po()
     arch, tensors = synth_tensors("1b", 2, 5)
     lens = [(7 * i + 3) % 40 + 1 for i in range(n_seq)]

@@ -9,7 +9,8 @@ from oracle import pyoracle as po   # rope table only (tools/ is test infrastruc
 name = sys.argv[1] if len(sys.argv) > 1 else "3b"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 arch = synth.preset(name, None)
-for S in (16, 2048):
+contexts = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [16, 2048]   # e.g. "2048" alone for an ncu capture
+for S in contexts:
     maxpos = S + 64
     eng = _capi.Engine(arch, po.rope_table(arch, maxpos), max_batch=B, max_positions=maxpos, page_size=16, max_prefill_tokens=B * S)
     for n, shape, scale, off in synth.tensor_specs(arch):
