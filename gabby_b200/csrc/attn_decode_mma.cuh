@@ -64,11 +64,19 @@ __global__ void __launch_bounds__(kAttnThreads, NBUF == 2 ? 3 : 2) attn_decode_m
         }
     }
 
-    auto issue_tile = [&](int jt, int buf) {   // tokens [jt, jt+16) of this warp -> K and V tiles of buffer `buf`
+    // Page indices of this warp's tiles, 32 at a time: lane k holds the block-table entry of the warp's (32 n + k)-th tile.
+    // Looking the page up when the tile is issued put one dependent L2 round trip (~0.7 us) in front of every tile's
+    // cp.async, which the in-order warp could not overlap with the MMAs of the tile before.
+    int my_page = 0;
+    auto load_pages = [&](int jt_base, int stride_tokens) {
+        const int jt = jt_base + lane * stride_tokens;
+        my_page = (page_tiles && jt < j1) ? bt[jt / a.kv.page_size] : 0;
+    };
+    auto issue_tile = [&](int jt, int buf, int ordinal) {   // tokens [jt, jt+16) of this warp -> K and V tiles of buffer `buf`
         uint16_t* sK = my_tiles + buf * 2 * TILE_ELEMS;
         uint16_t* sV = sK + TILE_ELEMS;
         if (page_tiles) {
-            const int page = bt[jt / a.kv.page_size], off0 = jt % a.kv.page_size;
+            const int page = __shfl_sync(0xffffffffu, my_page, ordinal & 31), off0 = jt % a.kv.page_size;
             const uint16_t* gK = a.kv.at(page, 0, off0) + kvh * HD;
             const uint16_t* gV = a.kv.at(page, 1, off0) + kvh * HD;
             const int last = j1 - 1 - jt;   // rows past the end repeat the last token (masked below)
@@ -100,18 +108,23 @@ __global__ void __launch_bounds__(kAttnThreads, NBUF == 2 ? 3 : 2) attn_decode_m
     const int stride = (a.interleave ? eff : 1) * kAttnWarps * TILE;
     int buf = 0;
     // prologue: NBUF - 1 tiles in flight (one commit group per tile slot, empty groups past the end keep the count uniform)
+    load_pages(first, stride);
+    int issued = 0;   // ordinal of the next tile to issue
 #pragma unroll
     for (int i = 0; i < NBUF - 1; i++) {
-        if (first + i * stride < j1) issue_tile(first + i * stride, i);
+        if (first + i * stride < j1) issue_tile(first + i * stride, i, issued);
         else asm volatile("cp.async.commit_group;" ::: "memory");
+        issued++;
     }
     for (int jt = first; jt < j1; jt += stride) {
         {
             const int nxt = jt + (NBUF - 1) * stride;
             int nb_ = buf + NBUF - 1;
             if (nb_ >= NBUF) nb_ -= NBUF;
-            if (nxt < j1) issue_tile(nxt, nb_);
+            if ((issued & 31) == 0) load_pages(nxt, stride);   // the next 32 tiles' pages (once per 512 x splits x 4 tokens)
+            if (nxt < j1) issue_tile(nxt, nb_, issued);
             else asm volatile("cp.async.commit_group;" ::: "memory");
+            issued++;
         }
         asm volatile("cp.async.wait_group %0;" ::"n"(NBUF - 1) : "memory");   // all but the NBUF - 1 newest groups: this tile has landed
         __syncwarp();
@@ -245,20 +258,60 @@ __global__ void __launch_bounds__(kAttnThreads, NBUF == 2 ? 3 : 2) attn_decode_m
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // The splits' (max, sum, acc) are fetched eight at a time with independent loads -- one L2 round trip per eight splits;
+    // the split-at-a-time loop made the last CTA pay two dependent round trips per split (~1.4 us each) after everyone else
+    // had finished. Same weights and the same fmaf order as before for <= 8 splits; chunks beyond are rescaled online.
+    // (three output elements per thread go through the loads together: 72 loads in flight per thread, then the arithmetic)
     const size_t rbase = (static_cast<size_t>(r) * nkv + kvh) * nsplit;
-    for (int e = tid; e < GROUP * HD; e += kAttnThreads) {
-        const int g = e / HD, d = e % HD;
-        float M = -INFINITY;
-        for (int s2 = 0; s2 < eff; s2++) M = fmaxf(M, __ldcg(a.part_ml + ((rbase + s2) * GROUP + g) * 2));
-        float L = 0.f, A = 0.f;
-        for (int s2 = 0; s2 < eff; s2++) {
-            const float ms = __ldcg(a.part_ml + ((rbase + s2) * GROUP + g) * 2);
-            if (ms == -INFINITY) continue;
-            const float w = __expf(ms - M);
-            L = fmaf(__ldcg(a.part_ml + ((rbase + s2) * GROUP + g) * 2 + 1), w, L);
-            A = fmaf(__ldcg(a.part_acc + ((rbase + s2) * GROUP + g) * HD + d), w, A);
+    constexpr int NE = (GROUP * HD + kAttnThreads - 1) / kAttnThreads, EB = 3;
+#pragma unroll 1
+    for (int k0 = 0; k0 < NE; k0 += EB) {
+        float M[EB], L[EB], A[EB];
+#pragma unroll
+        for (int k = 0; k < EB; k++) {
+            M[k] = -INFINITY;
+            L[k] = A[k] = 0.f;
         }
-        attn_store_out(a, r, (kvh * GROUP + g) * HD + d, A / L);
+        for (int base = 0; base < eff; base += 8) {
+            float2 ml[EB][8];
+            float av[EB][8];
+#pragma unroll
+            for (int k = 0; k < EB; k++) {
+                const int e = tid + (k0 + k) * kAttnThreads;
+                const int g = min(e, GROUP * HD - 1) / HD, d = min(e, GROUP * HD - 1) % HD;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int s2 = base + i;
+                    const bool ok = s2 < eff && e < GROUP * HD;
+                    const size_t pg = (rbase + (s2 < eff ? s2 : 0)) * GROUP + g;
+                    ml[k][i] = ok ? __ldcg(reinterpret_cast<const float2*>(a.part_ml + pg * 2)) : make_float2(-INFINITY, 0.f);
+                    av[k][i] = ok ? __ldcg(a.part_acc + pg * HD + d) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < EB; k++) {
+                float cm = M[k];
+#pragma unroll
+                for (int i = 0; i < 8; i++) cm = fmaxf(cm, ml[k][i].x);
+                if (cm == -INFINITY) continue;
+                const float keep = __expf(M[k] - cm);   // first chunk: exp(-inf) = 0 on L = A = 0
+                L[k] *= keep;
+                A[k] *= keep;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (ml[k][i].x == -INFINITY) continue;
+                    const float w = __expf(ml[k][i].x - cm);
+                    L[k] = fmaf(ml[k][i].y, w, L[k]);
+                    A[k] = fmaf(av[k][i], w, A[k]);
+                }
+                M[k] = cm;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < EB; k++) {
+            const int e = tid + (k0 + k) * kAttnThreads;
+            if (k0 + k < NE && e < GROUP * HD) attn_store_out(a, r, (kvh * GROUP + e / HD) * HD + e % HD, A[k] / L[k]);
+        }
     }
 }
 
