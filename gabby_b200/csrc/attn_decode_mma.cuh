@@ -6,8 +6,11 @@
 // double-buffered shared-memory tile, so warps never wait for each other), S = Q K^T and O += P V run on
 // the tensor cores. q (fp32, already scaled) and the probabilities are split into bf16 hi + lo parts and each
 // product is issued twice, so the result keeps the fp32-activation accuracy of the decode path
-// (error ~2^-16, same parity tolerances as the CUDA-core kernel). Same grid, partial-sum buffers and
-// last-arriver merge as attn_decode_kernel.
+// (error ~2^-16, same parity tolerances as the CUDA-core kernel). Same partial-sum buffers and last-arriver
+// merge as attn_decode_kernel; the launcher (engine.cu: attn_launch_hd) sizes the split count so that the
+// whole grid is resident in one wave (occupancy API). The 16-token tiles of a (row, kv head) are dealt
+// round-robin over all warps of all splits, each warp keeps NBUF - 1 tiles in flight and holds the page
+// indices of its next 32 tiles in its lanes; the last-arriving CTA merges the splits eight at a time.
 #pragma once
 #include "flash_prefill.cuh"
 

@@ -8,6 +8,9 @@
 // row tiles) enough CTAs to pull full HBM bandwidth; partials are summed by skinny_reduce_kernel
 // (deterministic order), which also applies the epilogue (store | residual add | SwiGLU).
 // Same warp roles and TMA/tcgen05 plumbing as gemm_tcgen05.cuh.
+// Fused reduce epilogues: skinny_reduce_rope_kv_kernel (QKV: + RoPE + K/V append into the paged cache),
+// skinny_reduce_norm_split_cluster_kernel (O / down on one GPU: + residual + the next RMSNorm + bf16 hi/lo split,
+// one thread-block cluster per activation row, sum of squares through distributed shared memory).
 #pragma once
 #include "gemm_tcgen05.cuh"
 #include "decode_kernels.cuh"
