@@ -23,6 +23,7 @@ CASES = [
     ("w1b_l2_s5", "1b", 2, 5, 12, 6),  # full 1B width (H=2048, V=128256), 2 layers
     ("w3b_l2_s34", "3b", 2, 34, 12, 6),  # Llama-3.2-3B width: H=3072, 24 query / 8 kv heads (GQA group 3), hd 128, tied head
     ("w8b_l2_s9", "8b", 2, 9, 12, 6),    # Llama-3.1-8B width: H=4096, I=14336, GQA group 4, untied lm_head, rope factor 8
+    ("w70b_l2_s71", "70b", 2, 71, 10, 4),  # Llama-3.1-70B width: H=8192, I=28672, 64 query / 8 kv heads (GQA group 8)
 ]
 
 

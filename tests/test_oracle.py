@@ -13,7 +13,9 @@ from gabby_b200 import synth
 from oracle import pyoracle as po
 from tests.helpers import load_golden, synth_tensors, cosine
 
-CASES = ["tiny_s1234", "tiny128_s77", "w1b_l2_s5", "w3b_l2_s34", "w8b_l2_s9"]   # the last two: GQA group 3 (3B) and the 8B width with Llama-3.1 rope scaling
+# w3b / w8b / w70b: two-layer variants at the Llama-3.2-3B (GQA group 3), Llama-3.1-8B (rope factor 8, untied head) and
+# Llama-3.1-70B (GQA group 8) widths -- the shapes of BASELINE configs[2..4]
+CASES = ["tiny_s1234", "tiny128_s77", "w1b_l2_s5", "w3b_l2_s34", "w8b_l2_s9", "w70b_l2_s71"]   
 LOGIT_ATOL = 5e-5   # fp32 vs fp32, different summation order
 HIDDEN_ATOL = 5e-5
 
